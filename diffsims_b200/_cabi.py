@@ -1,0 +1,57 @@
+"""ctypes binding of ``libdiffsims_b200.so`` (declared in include/diffsims_b200.h).
+
+This is the ONLY route from the Python API mirror to the sm_100a kernels.  There is no
+CPU fallback: a missing library or a missing CUDA device raises.
+"""
+import ctypes
+from ctypes import c_char_p, c_double, c_int32, c_void_p
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libdiffsims_b200.so"
+_lib = None
+
+# every symbol include/diffsims_b200.h declares
+SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_structure_factors", "ds_pack_gtable",
+           "ds_simulate", "ds_render")
+ABI_VERSION = 1
+
+
+class NativeLibraryError(ImportError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise NativeLibraryError(
+            f"{_LIB_PATH} is missing: build it with `python -m diffsims_b200.build` "
+            "(nvcc, sm_100a). diffsims_b200 has no CPU fallback.")
+    L = ctypes.CDLL(str(_LIB_PATH))
+    for s in SYMBOLS:
+        if not hasattr(L, s):
+            raise NativeLibraryError(f"{_LIB_PATH} does not export {s}")
+    L.ds_abi_version.restype = c_int32
+    L.ds_last_error.restype = c_char_p
+    if L.ds_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI version {L.ds_abi_version()} != {ABI_VERSION}: rebuild the library")
+    P, I, D = c_void_p, c_int32, c_double
+    L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P]
+    L.ds_pack_gtable.argtypes = [P, I, P, P]
+    L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P]
+    L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P]
+    for s in SYMBOLS[2:]:
+        getattr(L, s).restype = c_int32
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().ds_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())

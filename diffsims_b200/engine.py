@@ -1,0 +1,245 @@
+"""Device-level plumbing between the Python API mirror and the C-ABI kernels.
+
+torch is used for device memory, streams and host<->device copies only; every
+arithmetic stage of the hot path runs in libdiffsims_b200.so (K1 structure factors,
+K2 simulate, K3 render).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import json
+import math
+import warnings
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .crystal import get_element
+
+SHAPE_MODEL_IDS = {"binary": 0, "linear": 1, "sinc": 2, "sin2c": 3, "atanc": 4, "lorentzian": 5,
+                   "lorentzian_precession": 6, "return_s": 7}
+SCATTERING_IDS = {None: 0, "lobato": 1, "xtables": 2}
+
+_TABLES = None
+
+
+def scattering_tables():
+    global _TABLES
+    if _TABLES is None:
+        p = Path(__file__).resolve().parent / "data" / "scattering_params.json"
+        _TABLES = json.loads(p.read_text())
+    return _TABLES
+
+
+def get_scattering_params_dict(scattering_params):
+    """diffsims/utils/sim_utils.py:139-162."""
+    if scattering_params in ("lobato", "xtables"):
+        return scattering_tables()[scattering_params]
+    raise NotImplementedError(
+        "The scattering parameters `{}` are not implemented. "
+        "See documentation for available implementations.".format(scattering_params))
+
+
+def device(dev=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("diffsims_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _cabi.lib()
+    if dev is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def _stream():
+    return _cabi.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ----------------------------------------------------------------------------------------------
+# K1
+# ----------------------------------------------------------------------------------------------
+def atom_arrays(structure, debye_waller_factors, scattering_params):
+    """Host-side flattening of a structure, grouped by element.
+
+    Mirrors get_vectorized_list_for_atomic_scattering_factors (diffsims/utils/sim_utils.py:165-224)
+    -- including the warning + zero coefficients for unknown elements -- and the change of
+    reference frame of the fractional coordinates at :290-291.
+    """
+    if debye_waller_factors is None:
+        debye_waller_factors = {}
+    tbl = get_scattering_params_dict(scattering_params) if scattering_params is not None else {}
+    lat = structure.lattice
+    mat = np.linalg.inv(np.dot(np.asarray(lat.stdbase, float), np.asarray(lat.recbase, float)))
+    elements, groups = [], {}
+    for site in structure:
+        el = get_element(site.element)
+        if el not in groups:
+            groups[el] = []
+            elements.append(el)
+            if el not in tbl:
+                warnings.warn(f"Element {el} from atom type symbol {site.element} not "
+                              "found in scattering parameter library.")
+        groups[el].append(site)
+    frac, occ, start, coeffs, dw = [], [], [0], [], []
+    for el in elements:
+        for site in groups[el]:
+            frac.append(np.dot(np.asarray(site.xyz, float), mat))
+            occ.append(float(site.occupancy))
+        start.append(len(frac))
+        coeffs.append(np.asarray(tbl.get(el, np.zeros(10)), float).reshape(10))
+        dw.append(float(debye_waller_factors.get(el, 0)))
+    return (np.asarray(frac, float).reshape(-1, 3), np.asarray(occ, float), np.asarray(start, np.int32),
+            np.asarray(coeffs, float).reshape(-1, 10), np.asarray(dw, float))
+
+
+def structure_factors(structure, g_indices, g_hkls_array, debye_waller_factors=None,
+                      scattering_params="lobato", prefactor=None, dev=None, want_F=True, want_I=True):
+    """K1 on device. Returns (F [n,2] float64 tensor or None, I [n] float64 tensor or None)."""
+    if scattering_params not in SCATTERING_IDS:
+        raise NotImplementedError(
+            "The scattering parameters `{}` are not implemented. "
+            "See documentation for available implementations.".format(scattering_params))
+    dev = device(dev)
+    frac, occ, start, coeffs, dw = atom_arrays(structure, debye_waller_factors, scattering_params)
+    hkl = torch.as_tensor(np.ascontiguousarray(np.asarray(g_indices, float).reshape(-1, 3)), device=dev)
+    gn = torch.as_tensor(np.ascontiguousarray(np.asarray(g_hkls_array, float).reshape(-1)), device=dev)
+    n_g = hkl.shape[0]
+    if gn.shape[0] != n_g:
+        raise ValueError("g_indices and g_hkls_array must have the same length")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    frac_d, occ_d, start_d, coef_d, dw_d = t(frac), t(occ), t(start), t(coeffs), t(dw)
+    pre_d = None
+    if prefactor is not None and not np.isscalar(prefactor):
+        pre_d = t(np.broadcast_to(np.asarray(prefactor, float), (n_g,)))
+    F = torch.empty((n_g, 2), dtype=torch.float64, device=dev) if want_F else None
+    I = torch.empty((n_g,), dtype=torch.float64, device=dev) if want_I else None
+    rc = _cabi.lib().ds_structure_factors(
+        _stream(), n_g, _cabi.ptr(hkl), _cabi.ptr(gn), frac.shape[0], _cabi.ptr(frac_d), _cabi.ptr(occ_d),
+        coeffs.shape[0], _cabi.ptr(start_d), _cabi.ptr(coef_d), _cabi.ptr(dw_d),
+        SCATTERING_IDS[scattering_params], _cabi.ptr(pre_d), _cabi.ptr(F), _cabi.ptr(I))
+    _cabi.check(rc, "ds_structure_factors")
+    if I is not None and prefactor is not None and np.isscalar(prefactor) and prefactor != 1:
+        I *= float(prefactor)
+    return F, I
+
+
+# ----------------------------------------------------------------------------------------------
+# per-phase g table
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class GTable:
+    hkl: np.ndarray          # [n,3] integer Miller indices (host)
+    xyz_host: np.ndarray     # [n,3] float64 Cartesian g of the unrotated crystal (host)
+    xyz: torch.Tensor        # [n,3] float64 device
+    f32: torch.Tensor        # [n,4] float32 device (gx, gy, gz, |g|^2)
+    I0: torch.Tensor         # [n]   float64 device, |F(g)|^2
+    g_max: float
+
+    @property
+    def n(self):
+        return self.xyz.shape[0]
+
+
+def make_gtable(structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):
+    dev = device(dev)
+    hkl = np.ascontiguousarray(hkl)
+    xyz = np.ascontiguousarray(np.asarray(xyz, float))
+    gnorm = np.sqrt((xyz ** 2).sum(axis=1))
+    _, I0 = structure_factors(structure, hkl, gnorm, debye_waller_factors, scattering_params,
+                              dev=dev, want_F=False)
+    xyz_d = torch.as_tensor(xyz, device=dev)
+    f32 = torch.empty((xyz.shape[0], 4), dtype=torch.float32, device=dev)
+    _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), xyz.shape[0], _cabi.ptr(xyz_d), _cabi.ptr(f32)),
+                "ds_pack_gtable")
+    return GTable(hkl=hkl, xyz_host=xyz, xyz=xyz_d, f32=f32, I0=I0,
+                  g_max=float(gnorm.max()) if gnorm.size else 0.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# K2
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SpotTable:
+    """Padded per-rotation reflection lists on the device (row r holds count[r] entries)."""
+    count: torch.Tensor      # [n_rot] int32
+    g_index: torch.Tensor    # [n_rot, cap] int32
+    xyz: torch.Tensor        # [n_rot, cap, 3] float64
+    intensity: torch.Tensor  # [n_rot, cap] float64
+    exc: torch.Tensor | None
+    cap: int
+
+    @property
+    def n_rot(self):
+        return self.count.shape[0]
+
+
+def estimate_cap(n_g, g_max, s_max, precession_rad=0.0):
+    thick = s_max + 0.7 * g_max * abs(precession_rad)
+    mean = 1.5 * n_g * thick / max(g_max, 1e-6)
+    cap = int(8 * mean + 32)
+    cap = min(cap, n_g)
+    return max(32, (cap + 31) // 32 * 32)
+
+
+def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5.0,
+             precession_rad=0.0, min_intensity=1e-20, cap=None, want_exc=False, check_overflow=True):
+    """Run K2 for active unit quaternions ``quats`` ([n,4] float64; numpy or device tensor)."""
+    dev = gt.xyz.device
+    if isinstance(quats, torch.Tensor):
+        q = quats.to(device=dev, dtype=torch.float64).contiguous()
+    else:
+        q = torch.as_tensor(np.ascontiguousarray(np.asarray(quats, float).reshape(-1, 4)), device=dev)
+    n_rot = q.shape[0]
+    if cap is None:
+        cap = estimate_cap(gt.n, gt.g_max, s_max, precession_rad)
+    model_id = SHAPE_MODEL_IDS[model] if isinstance(model, str) else int(model)
+    while True:
+        count = torch.empty((n_rot,), dtype=torch.int32, device=dev)
+        g_index = torch.empty((n_rot, cap), dtype=torch.int32, device=dev)
+        xyz = torch.empty((n_rot, cap, 3), dtype=torch.float64, device=dev)
+        inten = torch.empty((n_rot, cap), dtype=torch.float64, device=dev)
+        exc = torch.empty((n_rot, cap), dtype=torch.float64, device=dev) if want_exc else None
+        max_count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        if gt.n == 0:
+            count.zero_()
+            return SpotTable(count, g_index, xyz, inten, exc, cap)
+        rc = _cabi.lib().ds_simulate(
+            _stream(), n_rot, _cabi.ptr(q), gt.n, _cabi.ptr(gt.xyz), _cabi.ptr(gt.f32), _cabi.ptr(gt.I0),
+            float(gt.g_max), 1.0 / float(wavelength), float(s_max), float(width), model_id,
+            float(minima_number), float(precession_rad), float(min_intensity), cap,
+            _cabi.ptr(count), _cabi.ptr(g_index), _cabi.ptr(xyz), _cabi.ptr(inten), _cabi.ptr(exc),
+            _cabi.ptr(max_count))
+        _cabi.check(rc, "ds_simulate")
+        if not check_overflow:
+            return SpotTable(count, g_index, xyz, inten, exc, cap)
+        need = int(max_count.item())
+        if need <= cap:
+            return SpotTable(count, g_index, xyz, inten, exc, cap)
+        cap = (need + 31) // 32 * 32
+
+
+# ----------------------------------------------------------------------------------------------
+# K3
+# ----------------------------------------------------------------------------------------------
+def gaussian_radius(sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter1d: lw = int(truncate * sd + 0.5)."""
+    return int(truncate * float(sigma) + 0.5)
+
+
+def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_angle=0.0, mirrored=False,
+           fast=True, normalize=True, clip_threshold=1.0, out=None):
+    """Run K3. ``count`` [n] int32, ``xyz`` [n,cap,3] f64, ``intensity`` [n,cap] f64 device tensors."""
+    dev = xyz.device
+    n, cap = intensity.shape
+    H, W = int(shape[0]), int(shape[1])
+    if out is None:
+        out = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == (n, H, W) and out.dtype == torch.float32 and out.is_contiguous()
+    rc = _cabi.lib().ds_render(
+        _stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), _cabi.ptr(intensity), H, W,
+        float(calibration), float(center[0]), float(center[1]), float(in_plane_angle), int(bool(mirrored)),
+        int(bool(fast)), float(sigma), gaussian_radius(sigma), float(clip_threshold), int(bool(normalize)),
+        _cabi.ptr(out))
+    _cabi.check(rc, "ds_render")
+    return out

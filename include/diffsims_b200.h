@@ -1,0 +1,136 @@
+/*
+ * diffsims_b200 -- C ABI of the B200-native kinematical template-simulation path.
+ *
+ * The reference (pyxem/diffsims 0.7.0) is pure Python and has no FFI seam; the
+ * boundary it offers is its Python API.  The Python
+ * mirror of that API in diffsims_b200/ reaches the sm_100a kernels ONLY through
+ * the entry points below (ctypes, tensor.data_ptr()).  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add at each cited call site.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the library never allocates or frees device memory and never synchronises:
+ *    work is enqueued on `stream` (a cudaStream_t, may be NULL = legacy stream);
+ *  - return value 0 = ok; negative = error (ds_last_error() gives the text);
+ *  - no C++ exceptions cross the boundary; no torch types appear here;
+ *  - doubles are IEEE binary64, row-major arrays, sizes in elements.
+ *
+ * All reference citations are relative to /root/reference.
+ */
+#ifndef DIFFSIMS_B200_H
+#define DIFFSIMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_ABI_VERSION 1
+
+/* atomic scattering factor parameterisations, diffsims/utils/sim_utils.py:227-253 */
+#define DS_SCATT_NONE    0 /* f = 1 for every atom (sim_utils.py:284-286)          */
+#define DS_SCATT_LOBATO  1 /* sum a_i (2 + b_i g^2) / (1 + b_i g^2)^2              */
+#define DS_SCATT_XTABLES 2 /* sum a_i exp(-b_i g^2 / 4)                             */
+
+/* rel-rod shape factors, diffsims/utils/shape_factor_models.py */
+#define DS_SHAPE_BINARY      0 /* :33-49   */
+#define DS_SHAPE_LINEAR      1 /* :52-73   */
+#define DS_SHAPE_SINC        2 /* :76-101  (0 at s == 0, as the reference's where= branch) */
+#define DS_SHAPE_SIN2C       3 /* :104-123 */
+#define DS_SHAPE_ATANC       4 /* :126-151 (1 at s == 0) */
+#define DS_SHAPE_LORENTZIAN  5 /* :154-180 */
+#define DS_SHAPE_LORENTZIAN_PRECESSION 6 /* :183-219, chosen when precession != 0 and approximate */
+#define DS_SHAPE_NONE_RETURN_S 7 /* prefactor 1, no threshold: caller applies a Python callable */
+
+int ds_abi_version(void);
+const char *ds_last_error(void);
+
+/*
+ * K1 -- kinematical structure factors, once per (phase, g-set).
+ * Replaces _get_kinematical_structure_factor (diffsims/utils/sim_utils.py:256-304),
+ * get_atomic_scattering_factors (:227-253) and the |F|^2 of
+ * get_kinematical_intensities (:307-354).
+ *
+ *   F(g) = sum_e f_e(g^2) exp(-g^2 B_e / 4) sum_{j in e} occ_j exp(2 pi i hkl . r_j)
+ *
+ * Atoms are grouped by element: atoms elem_start[e] .. elem_start[e+1]-1 belong to
+ * element e.  frac holds the fractional coordinates ALREADY multiplied by
+ * inv(stdbase @ recbase) (sim_utils.py:290-291; a 3x3 host-side matmul).
+ * Outputs (either may be NULL): F_out[n_g][2] = (re, im); I_out[n_g] =
+ * prefactor[g] * |F|^2 (prefactor NULL = 1).
+ */
+int ds_structure_factors(void *stream,
+                         int32_t n_g, const double *hkl /*[n_g][3]*/, const double *gnorm /*[n_g]*/,
+                         int32_t n_atoms, const double *frac /*[n_atoms][3]*/, const double *occ /*[n_atoms]*/,
+                         int32_t n_elem, const int32_t *elem_start /*[n_elem+1]*/,
+                         const double *coeffs /*[n_elem][5][2] (a_i, b_i)*/, const double *dw /*[n_elem]*/,
+                         int32_t scattering_model,
+                         const double *prefactor /*[n_g] or NULL*/,
+                         double *F_out /*[n_g][2] or NULL*/, double *I_out /*[n_g] or NULL*/);
+
+/*
+ * Pack the per-phase g table for K2: out[g] = (gx, gy, gz, |g|^2) as float (16-byte rows,
+ * the tile format K2 stages into shared memory with cp.async.bulk).
+ */
+int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz /*[n_g][3]*/, float *g_f32 /*[n_g][4]*/);
+
+/*
+ * K2 -- fused rotate / excitation error / shape factor / cull / threshold over
+ * (rotation x g).  Replaces the body of the rotation loop of
+ * SimulationGenerator.calculate_diffraction2d (diffsims/generators/simulation_generator.py:211-241):
+ * DiffractingVector.rotate_with_basis (crystallography/_diffracting_vector.py:127-161),
+ * get_intersecting_reflections (simulation_generator.py:319-412), the prefactor * |F|^2 of
+ * get_kinematical_intensities (utils/sim_utils.py:353) and the minimum_intensity threshold (:237);
+ * and likewise DiffractionGenerator.calculate_ed_data (generators/diffraction_generator.py:247-324).
+ *
+ *   g_lab = R(q) g,  R(q) the active rotation matrix of the unit quaternion q = (a, b, c, d)
+ *   s     = (r_s - sqrt(r_s^2 - x^2 - y^2)) - z,   r_s = inv_wavelength
+ *   keep  |s| < s_max (strict)           [precession: the two-surface test of :365-375]
+ *   I     = shape(s; width) * I0[g];     keep I > max_rot(I) * min_intensity
+ *
+ * Output is padded per rotation: row r holds count[r] reflections in g-table order,
+ * at most `cap`; *max_count (device int32, caller zero-initialised) receives the largest
+ * number of reflections any rotation needed, so the caller can retry with cap >= *max_count.
+ * excitation_error may be NULL.
+ */
+int ds_simulate(void *stream,
+                int32_t n_rot, const double *quat /*[n_rot][4]*/,
+                int32_t n_g, const double *g_xyz /*[n_g][3]*/, const float *g_f32 /*[n_g][4]*/,
+                const double *g_I0 /*[n_g]*/,
+                double g_max /* upper bound of |g| in the table (reciprocal radius) */,
+                double inv_wavelength, double s_max, double width,
+                int32_t shape_model, double minima_number, double precession_rad,
+                double min_intensity,
+                int32_t cap,
+                int32_t *count /*[n_rot]*/, int32_t *g_index /*[n_rot][cap]*/,
+                double *xyz /*[n_rot][cap][3]*/, double *intensity /*[n_rot][cap]*/,
+                double *excitation_error /*[n_rot][cap] or NULL*/,
+                int32_t *max_count /*[1]*/);
+
+/*
+ * K3 -- rasterise spot lists into templates.
+ * Replaces Simulation2D._get_transformed_coordinates (diffsims/simulations/simulation2d.py:261-285),
+ * the in-frame test / truncation / normalisation of get_diffraction_pattern (:357-442) and
+ * get_pattern_from_pixel_coordinates_and_intensities (diffsims/pattern/detector_functions.py:251-311):
+ *   fast != 0: integer pixels, last-write-wins assignment (:293-298) then scipy.ndimage.gaussian_filter
+ *              (separable, mode="reflect", taps exp(-k^2 / 2 sigma^2) / sum for |k| <= radius; the caller
+ *              passes radius = int(truncate * sigma + 0.5), scipy's rule with truncate = 4);
+ *   fast == 0: _subpixel_gaussian (:314-359), additive, clip box, no border folding.
+ * (DiffractionSimulation.get_diffraction_pattern, diffsims/sims/diffraction_simulation.py:296-354, is the
+ * same computation for square shapes: pattern[x, y] = I followed by .T.)
+ * images[n_tmpl][H][W] float32.  Rows of xyz are [cap][3] doubles (z ignored).
+ */
+int ds_render(void *stream,
+              int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
+              const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
+              int32_t H, int32_t W,
+              double calibration, double cx, double cy, double in_plane_angle_deg, int32_t mirrored,
+              int32_t fast, double sigma, int32_t radius,
+              double clip_threshold, int32_t normalize,
+              float *images /*[n_tmpl][H][W]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSIMS_B200_H */

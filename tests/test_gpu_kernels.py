@@ -1,0 +1,219 @@
+"""Parity of the three CUDA kernels (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import kinematical as K
+from tests.golden import cases
+from tests.helpers import (IMG_ATOL, RTOL, compare_spots, oracle_G_from_active_quat, random_quats, row)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from diffsims_b200 import engine
+    return engine
+
+
+# --------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("name", ["si", "graphite", "fe3c", "triclinic", "large"])
+@pytest.mark.parametrize("sp", ["lobato", "xtables", None])
+@pytest.mark.parametrize("aligned", [False, True])
+def test_structure_factors(eng, name, sp, aligned):
+    st = cases.phase(name).structure if aligned else cases.structure(name)
+    hkl = cases.hkl_box(4 if name != "large" else 3)
+    g = st.lattice.rnorm(hkl)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = K.kinematical_structure_factor(st, hkl, g, cases.DW, sp)
+        F, I = eng.structure_factors(st, hkl, g, cases.DW, sp)
+    F = F.cpu().numpy()
+    got = F[:, 0] + 1j * F[:, 1]
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-11 * scale)
+    np.testing.assert_allclose(I.cpu().numpy(), np.abs(ref) ** 2, rtol=1e-9, atol=1e-20 * scale ** 2)
+
+
+# --------------------------------------------------------------------------- K2
+def _gtable_new_api(eng, phase, rr, with_direct_beam, sp="lobato", dw=None):
+    st = phase.structure
+    gs = K.GSet(st, rr, with_direct_beam)
+    hkl, xyz = gs.hkl_int, gs.hkl_int @ st.lattice.recbase.T
+    if with_direct_beam:  # the reference appends a second (000), simulation_generator.py:351-353
+        hkl = np.vstack([hkl, [0, 0, 0]])
+        xyz = np.vstack([xyz, [0, 0, 0]])
+    return gs, eng.make_gtable(st, hkl, xyz, dw, sp)
+
+
+@pytest.mark.parametrize("name,kv,rr,s_max,model,db", [
+    ("si", 200, 1.0, 0.01, "lorentzian", True),
+    ("si", 200, 2.0, 0.05, "lorentzian", True),
+    ("si", 300, 5.0, 0.01, "lorentzian", True),
+    ("al", 200, 1.0, 0.01, "lorentzian", True),
+    ("ti", 300, 1.5, 0.02, "lorentzian", False),
+    ("graphite", 200, 1.6768, 0.1, "lorentzian", False),
+    ("fe3c", 200, 1.2, 0.03, "linear", True),
+    ("fe3c", 200, 1.2, 0.03, "sinc", True),
+    ("triclinic", 120, 1.0, 0.02, "sin2c", True),
+    ("triclinic", 120, 1.0, 0.02, "atanc", False),
+    ("fe_bcc", 200, 2.0, 0.01, "binary", True),
+])
+def test_simulate_matches_oracle(eng, name, kv, rr, s_max, model, db):
+    phase = cases.phase(name)
+    gs, gt = _gtable_new_api(eng, phase, rr, db)
+    wl = K.get_electron_wavelength(kv)
+    q = random_quats(24, 5)
+    q[0] = (1, 0, 0, 0)                                     # zone axis
+    q[1] = (np.cos(np.pi / 8), np.sin(np.pi / 8), 0, 0)     # 45 deg about x
+    spots = eng.simulate(gt, q, wl, s_max, s_max, model, want_exc=True)
+    total = 0
+    for r in range(len(q)):
+        ref = K.simulate_rotation(phase.structure, gs, oracle_G_from_active_quat(q[r]), wl, s_max,
+                                  K.SHAPE_FACTOR_MODELS[model])
+        total += compare_spots(ref, row(spots, r), s_max, rr)
+    assert total > 0
+
+
+def test_simulate_precession_approx(eng):
+    phase = cases.phase("si")
+    gs, gt = _gtable_new_api(eng, phase, 2.0, True)
+    wl = K.get_electron_wavelength(300)
+    q = random_quats(8, 9)
+    q[0] = (1, 0, 0, 0)
+    prec = np.deg2rad(0.5)
+    spots = eng.simulate(gt, q, wl, 0.01, 0.01, "lorentzian_precession", precession_rad=prec, want_exc=True)
+    for r in range(len(q)):
+        ref = K.simulate_rotation(phase.structure, gs, oracle_G_from_active_quat(q[r]), wl, 0.01,
+                                  precession_angle=0.5, approximate_precession=True)
+        compare_spots(ref, row(spots, r), 0.01, 2.0, prec=True)
+
+
+def test_simulate_reference_counts(eng):
+    """Si, 300 kV, rr = 5, [001]: 70 reflections incl. the duplicated (000); 250 with precession
+    (diffsims/tests/generators/test_simulation_generator.py:137-161)."""
+    phase = cases.phase("si")
+    gs, gt = _gtable_new_api(eng, phase, 5.0, True)
+    wl = K.get_electron_wavelength(300)
+    q = np.array([[1.0, 0, 0, 0]])
+    spots = eng.simulate(gt, q, wl, 0.01, 0.01, "lorentzian")
+    assert int(spots.count[0]) == 70
+    spots = eng.simulate(gt, q, wl, 0.01, 0.01, "lorentzian_precession", precession_rad=np.deg2rad(0.5))
+    assert int(spots.count[0]) == 250
+
+
+def test_simulate_streaming_tiles_large_cell(eng):
+    """N_g > 6144 exercises the double-buffered cp.async.bulk tile path."""
+    phase = cases.phase("large")
+    gs, gt = _gtable_new_api(eng, phase, 1.2, True, dw=cases.DW)
+    assert gt.n > 6144
+    wl = K.get_electron_wavelength(200)
+    q = random_quats(3, 11)
+    spots = eng.simulate(gt, q, wl, 0.01, 0.01, "lorentzian", want_exc=True)
+    for r in range(len(q)):
+        ref = K.simulate_rotation(phase.structure, gs, oracle_G_from_active_quat(q[r]), wl, 0.01,
+                                  debye_waller_factors=cases.DW)
+        compare_spots(ref, row(spots, r), 0.01, 1.2)
+
+
+def test_simulate_cap_overflow_retry(eng):
+    phase = cases.phase("si")
+    gs, gt = _gtable_new_api(eng, phase, 5.0, True)
+    wl = K.get_electron_wavelength(300)
+    q = np.array([[1.0, 0, 0, 0]])
+    spots = eng.simulate(gt, q, wl, 0.01, 0.01, "lorentzian", cap=32)
+    assert spots.cap >= 70 and int(spots.count[0]) == 70
+
+
+# --------------------------------------------------------------------------- K3
+def _render_one(eng, xyz, inten, shape, **kw):
+    import torch
+    n = len(inten)
+    cap = max(32, (n + 31) // 32 * 32)
+    X = np.zeros((1, cap, 3))
+    X[0, :n] = xyz
+    I = np.zeros((1, cap))
+    I[0, :n] = inten
+    dev = eng.device()
+    out = eng.render(torch.tensor([n], dtype=torch.int32, device=dev), torch.as_tensor(X, device=dev),
+                     torch.as_tensor(I, device=dev), shape, **kw)
+    return out[0].cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(cases.DETECTOR_CASES))
+@pytest.mark.parametrize("normalize", [True, False])
+def test_render_fast_matches_reference_golden(eng, golden_dir, name, normalize):
+    """detector.npz holds outputs of the reference's own integer-branch rasteriser."""
+    shape, sigma, n, seed = cases.DETECTOR_CASES[name]
+    xy, inten = cases.detector_spots(shape, n, seed)
+    ref = np.load(golden_dir / "detector.npz")[f"{name}_int"]
+    if normalize:
+        ref = ref / ref.max()
+    xyz = np.concatenate([xy, np.zeros((n, 1))], axis=1)
+    got = _render_one(eng, xyz, inten, shape, sigma=sigma, calibration=1.0, center=(0.0, 0.0),
+                      fast=True, normalize=normalize)
+    assert np.abs(got - ref).max() <= IMG_ATOL * ref.max()
+
+
+@pytest.mark.parametrize("name", list(cases.DETECTOR_CASES))
+def test_render_slow_matches_reference_golden(eng, golden_dir, name):
+    shape, sigma, n, seed = cases.DETECTOR_CASES[name]
+    xy, inten = cases.detector_spots(shape, n, seed)
+    ref = np.load(golden_dir / "detector.npz")[f"{name}_float"]
+    xyz = np.concatenate([xy, np.zeros((n, 1))], axis=1)
+    got = _render_one(eng, xyz, inten * 2000.0, shape, sigma=sigma, calibration=1.0, center=(0.0, 0.0),
+                      fast=False, normalize=False, clip_threshold=1.0)
+    assert np.abs(got - ref).max() <= IMG_ATOL * ref.max()
+
+
+@pytest.mark.parametrize("shape,sigma,cal,angle,mirrored,fast", [
+    ((256, 256), 10, 1 / 128, 0, False, True),
+    ((256, 256), 1.4, 1 / 128, 30, True, True),
+    ((144, 144), 10, 0.01, 0, False, True),
+    ((100, 180), 3, 0.012, 77.5, False, True),
+    ((256, 256), 4, 1 / 128, 12, True, False),
+    ((144, 144), 10, 0.01, 0, False, False),
+])
+def test_render_matches_oracle_on_simulated_spots(eng, shape, sigma, cal, angle, mirrored, fast):
+    phase = cases.phase("si")
+    gs = K.GSet(phase.structure, 1.0, True)
+    wl = K.get_electron_wavelength(200)
+    for seed in range(3):
+        G = oracle_G_from_active_quat(random_quats(1, seed)[0]) if seed else np.eye(3)
+        r = K.simulate_rotation(phase.structure, gs, G, wl, 0.02)
+        inten = r["intensity"] * (1.0 if fast else 50.0)
+        center = (shape[1] // 2, shape[0] // 2) if fast else ((shape[1] - 1) / 2, (shape[0] - 1) / 2)
+        ref = K.diffraction_pattern(r["xyz"], inten, shape, sigma=sigma, in_plane_angle=angle,
+                                    calibration=cal, mirrored=mirrored, fast=fast, normalize=True)
+        got = _render_one(eng, r["xyz"], inten, shape, sigma=sigma, calibration=cal, center=center,
+                          in_plane_angle=angle, mirrored=mirrored, fast=fast, normalize=True)
+        assert np.nanmax(np.abs(got - ref)) <= IMG_ATOL
+
+
+def test_render_empty_is_zero(eng):
+    got = _render_one(eng, np.zeros((0, 3)), np.zeros(0), (64, 64), sigma=3, calibration=0.01,
+                      center=(32, 32), fast=True, normalize=True)
+    assert np.all(got == 0)
+    # all spots out of frame
+    got = _render_one(eng, np.array([[5.0, 5.0, 0]]), np.array([1.0]), (64, 64), sigma=3, calibration=0.01,
+                      center=(32, 32), fast=True, normalize=True)
+    assert np.all(got == 0)
+
+
+def test_render_graphite_golden(eng, golden_dir):
+    """The reference's strongest pin (test_simulation_generator.py:283-343) through K2 + K3."""
+    phase = cases.phase("graphite")
+    gs, gt = _gtable_new_api(eng, phase, 1.6768, False)
+    wl = K.get_electron_wavelength(200)
+    G = K.bunge_matrix(*np.deg2rad([0, 90, 90]))
+    from diffsims_b200.crystal import Rotation
+    q = (~Rotation.from_euler([[0, 90, 90]], degrees=True)).data
+    spots = eng.simulate(gt, q, wl, 0.1, 0.1, "lorentzian")
+    assert int(spots.count[0]) == 104
+    img = eng.render(spots.count, spots.xyz, spots.intensity, (128, 128), sigma=1.4, calibration=0.0262,
+                     center=(64, 64))[0].cpu().numpy()
+    old = np.load(golden_dir / "old_simulation.npz")["image"]
+    assert np.abs(img - old).max() <= IMG_ATOL
