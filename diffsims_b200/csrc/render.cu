@@ -18,9 +18,13 @@
 // Output is written exactly once with coalesced 16-byte stores: the kernel's algorithmic traffic is
 // H*W*4 bytes per template and it is HBM-write bound; normalisation by the template maximum is done by
 // recomputing the register tiles in a second pass instead of re-reading the image.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ds {
+
+int num_sms();
 
 constexpr int RN_WARPS = 8;
 constexpr int RN_THREADS = RN_WARPS * 32;
@@ -55,8 +59,7 @@ struct FastSmem {
 
 __device__ __forceinline__ FastSmem carve_fast(unsigned char *base, const RenderParams &p) {
     FastSmem s;
-    s.lut = reinterpret_cast<float4 *>(base);
-    base += (size_t)4 * p.n4 * sizeof(float4);
+    s.lut = nullptr;  // CTA-wide, set by the kernel
     s.hash = reinterpret_cast<unsigned long long *>(base);
     base += (size_t)p.table_size * 8;
     s.key = reinterpret_cast<int *>(base);
@@ -71,33 +74,48 @@ __device__ __forceinline__ FastSmem carve_fast(unsigned char *base, const Render
     return s;
 }
 
-static size_t fast_smem_bytes(int cap, int n4, int table_size) {
-    return (size_t)4 * n4 * 16 + (size_t)table_size * 8 + (size_t)cap * 16;
-}
 
-// LUT fetch: 4 consecutive taps L[d .. d+3] of the zero-padded symmetric kernel, any integer offset d.
-__device__ __forceinline__ float4 fetch4(const float4 *lut, int n4, int radius, int d) {
-    d = max(-(radius + 4), min(d, radius + 1));  // outside the support every tap is 0
-    const int a = d + radius + 4;
-    return lut[(a & 3) * n4 + (a >> 2)];
+// LUT layout.  The padded symmetric kernel is L[a] = w[|a - (R + 8)|] (0 outside the support).  Copy k
+// (k = 0..3) holds float4 entries i -> (L[4i+k] .. L[4i+k+3]), so four consecutive taps at ANY integer
+// offset are one aligned LDS.128: offset d -> a = d + R + 8, copy a & 3, entry a >> 2 clamped to
+// [0, n4 - 1] (both end entries are all zero).  Lanes of a quarter warp read consecutive entries.
+__device__ __forceinline__ float4 fetch4(const float4 *lut, int n4, int R, int d) {
+    const int a = d + R + 8;
+    const int i = min(max(a >> 2, 0), n4 - 1);
+    return lut[(a & 3) * n4 + i];
+}
+__device__ __forceinline__ float tap(const float4 *lut, int n4, int R, int d) {  // w[|d|], 0 outside
+    return fetch4(lut, n4, R, d).x;
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
-// Folded weights of 4 consecutive pixels p0..p0+3 for a delta at pixel `c` on an axis of length n.
-__device__ __forceinline__ float4 folded4(const float4 *lut, int n4, int radius, int p0, int c, int n) {
-    float4 w = fetch4(lut, n4, radius, p0 - c);
-    if (c < radius) w = add4(w, fetch4(lut, n4, radius, p0 + c + 1));               // left/top mirror image
-    if (c >= n - radius) w = add4(w, fetch4(lut, n4, radius, p0 + c + 1 - 2 * n));  // right/bottom mirror
-    if (radius >= n) {  // kernel wider than the axis: further images at c + 2 n m and -c - 1 + 2 n m
-        const int M = radius / n + 1;
+// Folded weights of 4 consecutive pixels p0..p0+3 for a delta at pixel `c` on an axis of length n:
+// direct tap + the mirror images of scipy's mode="reflect" (... d c b a | a b c d | d c b a ...).
+template <bool WIDE>
+__device__ __forceinline__ float4 folded4(const float4 *lut, int n4, int R, int p0, int c, int n) {
+    float4 w = fetch4(lut, n4, R, p0 - c);
+    if (!WIDE) {
+        if (c < R) w = add4(w, fetch4(lut, n4, R, p0 + c + 1));               // image at -c - 1
+        if (c >= n - R) w = add4(w, fetch4(lut, n4, R, p0 + c + 1 - 2 * n));  // image at 2n - 1 - c
+    } else {  // kernel wider than the axis: images at c + 2 n m and -c - 1 + 2 n m
+        const int M = R / n + 1;
         for (int m = -M; m <= M; ++m) {
-            if (m != 0) w = add4(w, fetch4(lut, n4, radius, p0 - (c + 2 * n * m)));
-            if (m != 0 && m != 1) w = add4(w, fetch4(lut, n4, radius, p0 - (-c - 1 + 2 * n * m)));
+            if (m != 0) w = add4(w, fetch4(lut, n4, R, p0 - (c + 2 * n * m)));
+            w = add4(w, fetch4(lut, n4, R, p0 - (-c - 1 + 2 * n * m)));
         }
     }
     return w;
+}
+
+// Upper bound of the folded weight over the pixel interval [lo, hi] (taps decrease with distance).
+__device__ __forceinline__ float folded_bound(const float4 *lut, int n4, int R, int lo, int hi, int c, int n) {
+    auto dist = [&](int pos) { return pos < lo ? lo - pos : (pos > hi ? pos - hi : 0); };
+    float b = tap(lut, n4, R, dist(c));
+    if (c < R) b += tap(lut, n4, R, dist(-c - 1));
+    if (c >= n - R) b += tap(lut, n4, R, dist(2 * n - 1 - c));
+    return b;
 }
 
 __device__ __forceinline__ void fma_tile(float (&acc)[8][8], const float (&wy)[8], const float (&wx)[8]) {
@@ -108,38 +126,59 @@ __device__ __forceinline__ void fma_tile(float (&acc)[8][8], const float (&wy)[8
 }
 
 // One warp region (64 x 32 px at rx0, ry0): accumulate all live spots into the lane's 8 x 8 tile.
-__device__ __forceinline__ void accumulate_fast(const RenderParams &p, const FastSmem &s, int n_live, int rx0,
+// Returns false (acc untouched) when no spot reaches the region.
+template <bool WIDE>
+__device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const FastSmem &s, int n_live, int rx0,
                                                 int ry0, int lane, float (&acc)[8][8]) {
     const int lx = lane & 7, ly = lane >> 3;
     const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
     const int R = p.radius;
-    const bool wide = (R >= p.W) || (R >= p.H);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    bool any = false;
     for (int base = 0; base < n_live; base += 32) {
         const int j = base + lane;
         bool hit = false;
         if (j < n_live) {
-            const int sx = s.ix[j], sy = s.iy[j];
-            hit = wide || (sx + R >= rx0 && sx - R < rx0 + RN_RW && sy + R >= ry0 && sy - R < ry0 + RN_RH);
+            const int sx = s.ix[j], sy = s.iy[j] & 0x3fff;
+            hit = WIDE || (sx + R >= rx0 && sx - R < rx0 + RN_RW && sy + R >= ry0 && sy - R < ry0 + RN_RH);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask && !any) {
+            any = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
+        }
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int sx = s.ix[base + b], sy = s.iy[base + b];
+            const int sx = s.ix[base + b], syf = s.iy[base + b];
+            const int sy = syf & 0x3fff;
             const float a = s.amp[base + b];
-            const float4 xa = folded4(s.lut, p.n4, R, x0, sx, p.W);
-            const float4 xb = folded4(s.lut, p.n4, R, x0 + 32, sx, p.W);
-            const float4 ya = folded4(s.lut, p.n4, R, y0, sy, p.H);
-            const float4 yb = folded4(s.lut, p.n4, R, y0 + 4, sy, p.H);
+            float4 xa, xb, ya, yb;
+            if (WIDE) {
+                xa = folded4<true>(s.lut, p.n4, R, x0, sx, p.W);
+                xb = folded4<true>(s.lut, p.n4, R, x0 + 32, sx, p.W);
+                ya = folded4<true>(s.lut, p.n4, R, y0, sy, p.H);
+                yb = folded4<true>(s.lut, p.n4, R, y0 + 4, sy, p.H);
+            } else {
+                xa = fetch4(s.lut, p.n4, R, x0 - sx);
+                xb = fetch4(s.lut, p.n4, R, x0 + 32 - sx);
+                ya = fetch4(s.lut, p.n4, R, y0 - sy);
+                yb = fetch4(s.lut, p.n4, R, y0 + 4 - sy);
+                if (syf & 0x4000) {  // the box crosses a border: add the reflect-folded images
+                    xa = folded4<false>(s.lut, p.n4, R, x0, sx, p.W);
+                    xb = folded4<false>(s.lut, p.n4, R, x0 + 32, sx, p.W);
+                    ya = folded4<false>(s.lut, p.n4, R, y0, sy, p.H);
+                    yb = folded4<false>(s.lut, p.n4, R, y0 + 4, sy, p.H);
+                }
+            }
             const float wx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
             const float wy[8] = {a * ya.x, a * ya.y, a * ya.z, a * ya.w, a * yb.x, a * yb.y, a * yb.z, a * yb.w};
             fma_tile(acc, wy, wx);
         }
     }
+    return any;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -162,21 +201,25 @@ __device__ __forceinline__ SlowSmem carve_slow(unsigned char *base, const Render
 }
 static size_t slow_smem_bytes(int cap) { return (size_t)cap * 20; }
 
-__device__ __forceinline__ void accumulate_slow(const RenderParams &p, const SlowSmem &s, int n_live, int rx0,
+__device__ __forceinline__ bool accumulate_slow(const RenderParams &p, const SlowSmem &s, int n_live, int rx0,
                                                 int ry0, int lane, float (&acc)[8][8]) {
     const int lx = lane & 7, ly = lane >> 3;
     const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
     const float ef = (float)(-1.0 / (2.0 * p.sigma * p.sigma));
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    bool any = false;
     for (int base = 0; base < n_live; base += 32) {
         const int j = base + lane;
         bool hit = false;
         if (j < n_live)
             hit = s.xhi[j] >= rx0 && s.xlo[j] < rx0 + RN_RW && s.yhi[j] >= ry0 && s.ylo[j] < ry0 + RN_RH;
         unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask && !any) {
+            any = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
+        }
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -196,25 +239,43 @@ __device__ __forceinline__ void accumulate_slow(const RenderParams &p, const Slo
             fma_tile(acc, wy, wx);
         }
     }
+    return any;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------
-template <bool FAST>
-__global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_n_live, s_n_inframe;
-    __shared__ float s_wmax[RN_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x;
+// A "group" of G warps (G = 1, 2, 4 or 8) owns one template at a time; a CTA holds 8 / G groups and is
+// persistent (loops over templates with a grid stride).  G = 1 keeps 8 independent templates in flight per
+// CTA with no block-wide barriers at all (sparse patterns are latency-, not throughput-bound); larger G
+// spreads the regions of one dense template over more warps.  Groups synchronise on named barriers.
+template <int G>
+__device__ __forceinline__ void group_sync(int group) {
+    if (G == 1) {
+        __syncwarp();
+    } else if (G == RN_WARPS) {
+        __syncthreads();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(G * 32) : "memory");
+    }
+}
 
-    FastSmem fs;
-    SlowSmem ss;
+template <bool FAST, int G, bool WIDE, bool VEC>
+__global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParams p, const int group_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NGROUPS = RN_WARPS / G;
+    constexpr int GT = G * 32;  // threads per group
+    __shared__ int s_n_live[NGROUPS], s_n_inframe[NGROUPS];
+    __shared__ float s_wmax[RN_WARPS];
+    __shared__ double s_norm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp / G, gwarp = warp % G, gtid = gwarp * 32 + lane;
+
+    // ---- CTA-wide, once: the 4-way shifted LUT of the normalised 1-D taps --------------------------------
+    // scipy.ndimage._gaussian_kernel1d: exp(-0.5 k^2 / sigma^2) / sum over |k| <= radius
+    float4 *lut = reinterpret_cast<float4 *>(smem_raw);
+    unsigned char *gbase = smem_raw + (FAST ? (size_t)4 * p.n4 * sizeof(float4) : 0) + (size_t)group * group_bytes;
     if (FAST) {
-        fs = carve_fast(smem_raw, p);
-        // normalised 1-D taps, scipy.ndimage._gaussian_kernel1d: exp(-0.5 k^2 / sigma^2) / sum
-        __shared__ double s_norm;
         if (warp == 0) {
             double part = 0.0;
             for (int k = lane; k <= p.radius; k += 32)
@@ -225,182 +286,267 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         }
         __syncthreads();
         const double inv = 1.0 / s_norm;
-        float *lutf = reinterpret_cast<float *>(fs.lut);
+        float *lutf = reinterpret_cast<float *>(lut);
         for (int e = threadIdx.x; e < 16 * p.n4; e += RN_THREADS) {
             const int copy = e / (4 * p.n4), rem = e % (4 * p.n4);
             const int a = (rem >> 2) * 4 + copy + (rem & 3);  // position in the padded kernel
-            const int k = abs(a - (p.radius + 4));
+            const int k = abs(a - (p.radius + 8));
             lutf[e] = (k <= p.radius) ? (float)(exp(-0.5 / (p.sigma * p.sigma) * (double)k * (double)k) * inv) : 0.f;
         }
-        for (int e = threadIdx.x; e < p.table_size; e += RN_THREADS) fs.hash[e] = 0ull;
-    } else {
-        ss = carve_slow(smem_raw, p);
-    }
-    if (threadIdx.x == 0) s_n_live = s_n_inframe = 0;
-    __syncthreads();
-
-    // ---- project spots to detector pixels (simulation2d.py:261-285, :422-430), float64 ---------------
-    const int n = min(p.count[t], p.cap);
-    const size_t row = (size_t)t * p.cap;
-    if (FAST) {
-        for (int j = threadIdx.x; j < n; j += RN_THREADS) {
-            const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
-            // r cos(+-atan2(y, x) + a) + cx written without the polar round trip
-            const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-            const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
-            int key = -1;
-            if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
-                key = (int)py * p.W + (int)px;  // astype(int): truncation
-                // last write wins (detector_functions.py:297): keep the largest spot index per pixel
-                const unsigned long long packed = ((unsigned long long)(key + 1) << 32) | (unsigned)j;
-                unsigned h = ((unsigned)key * 2654435761u) & (p.table_size - 1);
-                while (true) {
-                    unsigned long long cur = fs.hash[h];
-                    if (cur == 0ull) {
-                        const unsigned long long old = atomicCAS(&fs.hash[h], 0ull, packed);
-                        if (old == 0ull) break;
-                        cur = old;
-                    }
-                    if ((cur >> 32) == (unsigned long long)(key + 1)) {
-                        atomicMax(&fs.hash[h], packed);
-                        break;
-                    }
-                    h = (h + 1) & (p.table_size - 1);
-                }
-            }
-            fs.key[j] = key;
-            fs.inten[j] = (float)p.intensity[row + j];
-        }
         __syncthreads();
-        if (warp == 0) {  // deterministic compaction of the surviving spots
-            int n_live = 0;
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                bool live = false;
-                int key = -1;
-                if (j < n && (key = fs.key[j]) >= 0) {
-                    unsigned h = ((unsigned)key * 2654435761u) & (p.table_size - 1);
-                    while ((fs.hash[h] >> 32) != (unsigned long long)(key + 1)) h = (h + 1) & (p.table_size - 1);
-                    live = (unsigned)(fs.hash[h] & 0xffffffffu) == (unsigned)j;
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const int d = n_live + __popc(mask & ((1u << lane) - 1u));
-                    fs.ix[d] = (short)(key % p.W);
-                    fs.iy[d] = (short)(key / p.W);
-                    fs.amp[d] = fs.inten[j];
-                }
-                n_live += __popc(mask);
-            }
-            if (lane == 0) s_n_live = n_live;
-        }
-    } else {
-        if (warp == 0) {
-            const double pref = 1.0 / (2.0 * 3.141592653589793 * p.sigma * p.sigma);
-            const double ef = -1.0 / (2.0 * p.sigma * p.sigma);
-            int n_live = 0, n_in = 0;
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                bool live = false, inframe = false;
-                double px = 0, py = 0, I = 0, rad = 0;
-                if (j < n) {
-                    const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
-                    px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-                    py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
-                    I = p.intensity[row + j];
-                    if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
-                        inframe = true;
-                        rad = sqrt(log(p.clip / (pref * I)) / ef);  // detector_functions.py:339
-                        live = !isnan(rad);
-                    }
-                }
-                n_in += __popc(__ballot_sync(0xffffffffu, inframe));
-                const unsigned mask = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const int d = n_live + __popc(mask & ((1u << lane) - 1u));
-                    ss.fx[d] = (float)px;
-                    ss.fy[d] = (float)py;
-                    ss.amp[d] = (float)(I * pref);
-                    // slices :343-352: [max(0, ceil(c - r)), min(n, floor(c + r + 1)))
-                    ss.xlo[d] = (short)max(0, (int)fmin(ceil(px - rad), 32000.0));
-                    ss.xhi[d] = (short)(min(p.W, (int)fmin(floor(px + rad + 1.0), 32000.0)) - 1);
-                    ss.ylo[d] = (short)max(0, (int)fmin(ceil(py - rad), 32000.0));
-                    ss.yhi[d] = (short)(min(p.H, (int)fmin(floor(py + rad + 1.0), 32000.0)) - 1);
-                }
-                n_live += __popc(mask);
-            }
-            if (lane == 0) {
-                s_n_live = n_live;
-                s_n_inframe = n_in;
-            }
-        }
     }
-    __syncthreads();
-    const int n_live = s_n_live;
+    FastSmem fs;
+    SlowSmem ss;
+    unsigned char *flags;  // [n_regions] 1 = the region can hold the template maximum
+    if (FAST) {
+        fs = carve_fast(gbase, p);
+        fs.lut = lut;
+        flags = reinterpret_cast<unsigned char *>(fs.iy + p.cap);
+    } else {
+        ss = carve_slow(gbase, p);
+        flags = reinterpret_cast<unsigned char *>(ss.yhi + p.cap);
+    }
 
     const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
     const int n_regions = nrx * nry;
-    float *img = p.images + (size_t)t * p.H * p.W;
     const int lx = lane & 7, ly = lane >> 3;
-    const bool vec_ok = (p.W & 3) == 0;
 
-    float scale = 1.f;
-    // reference: no spot in frame -> zeros, returned before the normalisation (simulation2d.py:434-435)
-    // (the test is on the IN-FRAME spots; slow-path spots skipped for a NaN radius still count, so an
-    // all-skipped pattern is 0 / 0 = NaN in the reference and here)
-    const int n_pass = (p.normalize && (FAST ? n_live > 0 : s_n_inframe > 0)) ? 2 : 1;
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const bool store = (pass == n_pass - 1);
-        float vmax = -INFINITY;
-        for (int reg = warp; reg < n_regions; reg += RN_WARPS) {
-            const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
-            float acc[8][8];
-            if (FAST)
-                accumulate_fast(p, fs, n_live, rx0, ry0, lane, acc);
-            else
-                accumulate_slow(p, ss, n_live, rx0, ry0, lane, acc);
-            const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
-            if (!store) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int x = x0 + (j & 3) + (j >> 2) * 32, y = y0 + i;
-                        if (x < p.W && y < p.H) vmax = fmaxf(vmax, acc[i][j]);
+    for (int t = blockIdx.x * NGROUPS + group; t < p.n_tmpl; t += gridDim.x * NGROUPS) {
+        // ---- project spots to detector pixels (simulation2d.py:261-285, :422-430), float64 -----------
+        const int n = min(p.count[t], p.cap);
+        const size_t row = (size_t)t * p.cap;
+        if (FAST) {
+            for (int e = gtid; e < p.table_size; e += GT) fs.hash[e] = 0ull;
+            group_sync<G>(group);
+            for (int j = gtid; j < n; j += GT) {
+                const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
+                // r cos(+-atan2(y, x) + a) + cx written without the polar round trip
+                const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
+                const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+                int key = -1;
+                if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
+                    key = (int)py * p.W + (int)px;  // astype(int): truncation
+                    // last write wins (detector_functions.py:297): keep the largest spot index per pixel
+                    const unsigned long long packed = ((unsigned long long)(key + 1) << 32) | (unsigned)j;
+                    unsigned h = ((unsigned)key * 2654435761u) & (p.table_size - 1);
+                    while (true) {
+                        unsigned long long cur = fs.hash[h];
+                        if (cur == 0ull) {
+                            const unsigned long long old = atomicCAS(&fs.hash[h], 0ull, packed);
+                            if (old == 0ull) break;
+                            cur = old;
+                        }
+                        if ((cur >> 32) == (unsigned long long)(key + 1)) {
+                            atomicMax(&fs.hash[h], packed);
+                            break;
+                        }
+                        h = (h + 1) & (p.table_size - 1);
                     }
-            } else {
+                }
+                fs.key[j] = key;
+                fs.inten[j] = (float)p.intensity[row + j];
+            }
+            group_sync<G>(group);
+            if (gwarp == 0) {  // deterministic compaction of the surviving spots
+                int n_live = 0;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool live = false;
+                    int key = -1;
+                    if (j < n && (key = fs.key[j]) >= 0) {
+                        unsigned h = ((unsigned)key * 2654435761u) & (p.table_size - 1);
+                        while ((fs.hash[h] >> 32) != (unsigned long long)(key + 1)) h = (h + 1) & (p.table_size - 1);
+                        live = (unsigned)(fs.hash[h] & 0xffffffffu) == (unsigned)j;
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, live);
+                    if (live) {
+                        const int d = n_live + __popc(mask & ((1u << lane) - 1u));
+                        const int sx = key % p.W, sy = key / p.W;
+                        const bool fold = sx < p.radius || sx >= p.W - p.radius || sy < p.radius || sy >= p.H - p.radius;
+                        fs.ix[d] = (short)sx;
+                        fs.iy[d] = (short)(sy | (fold ? 0x4000 : 0));
+                        fs.amp[d] = fs.inten[j];
+                    }
+                    n_live += __popc(mask);
+                }
+                if (lane == 0) s_n_live[group] = s_n_inframe[group] = n_live;
+            }
+        } else {
+            if (gwarp == 0) {
+                const double pref = 1.0 / (2.0 * 3.141592653589793 * p.sigma * p.sigma);
+                const double ef = -1.0 / (2.0 * p.sigma * p.sigma);
+                int n_live = 0, n_in = 0;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool live = false, inframe = false;
+                    double px = 0, py = 0, I = 0, rad = 0;
+                    if (j < n) {
+                        const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
+                        px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
+                        py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+                        I = p.intensity[row + j];
+                        if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
+                            inframe = true;
+                            rad = sqrt(log(p.clip / (pref * I)) / ef);  // detector_functions.py:339
+                            live = !isnan(rad);
+                        }
+                    }
+                    n_in += __popc(__ballot_sync(0xffffffffu, inframe));
+                    const unsigned mask = __ballot_sync(0xffffffffu, live);
+                    if (live) {
+                        const int d = n_live + __popc(mask & ((1u << lane) - 1u));
+                        ss.fx[d] = (float)px;
+                        ss.fy[d] = (float)py;
+                        ss.amp[d] = (float)(I * pref);
+                        // slices :343-352: [max(0, ceil(c - r)), min(n, floor(c + r + 1)))
+                        ss.xlo[d] = (short)max(0, (int)fmin(ceil(px - rad), 32000.0));
+                        ss.xhi[d] = (short)(min(p.W, (int)fmin(floor(px + rad + 1.0), 32000.0)) - 1);
+                        ss.ylo[d] = (short)max(0, (int)fmin(ceil(py - rad), 32000.0));
+                        ss.yhi[d] = (short)(min(p.H, (int)fmin(floor(py + rad + 1.0), 32000.0)) - 1);
+                    }
+                    n_live += __popc(mask);
+                }
+                if (lane == 0) {
+                    s_n_live[group] = n_live;
+                    s_n_inframe[group] = n_in;
+                }
+            }
+        }
+        group_sync<G>(group);
+        const int n_live = s_n_live[group];
+        float *img = p.images + (size_t)t * p.H * p.W;
+
+        // reference: no spot in frame -> zeros, returned before the normalisation (simulation2d.py:434-435)
+        // (the test is on the IN-FRAME spots; slow-path spots skipped for a NaN radius still count, so an
+        // all-skipped pattern is 0 / 0 = NaN in the reference and here)
+        const int n_pass = (p.normalize && s_n_inframe[group] > 0) ? 2 : 1;
+
+        if (n_pass == 2) {
+            // ---- which regions can hold the maximum?  A region whose upper bound sum_s a_s max(Wy) max(Wx)
+            // is below a lower bound of the maximum (the strongest spot's own centre tap) is skipped by the
+            // max pass.  With a direct beam this leaves the few regions around it.
+            bool prune = FAST && !WIDE;
+            float lower = 0.f;
+            if (prune) {
+                float amin = INFINITY, amax = -INFINITY;
+                for (int j = lane; j < n_live; j += 32) {
+                    amin = fminf(amin, fs.amp[j]);
+                    amax = fmaxf(amax, fs.amp[j]);
+                }
+                amin = -warp_max(-amin);
+                amax = warp_max(amax);
+                const float w0 = tap(lut, p.n4, p.radius, 0);
+                lower = amax * w0 * w0;
+                prune = amin >= 0.f && lower > 0.f;  // (NaN amplitudes fail both tests)
+            }
+            for (int reg = gtid; reg < n_regions; reg += GT) {
+                unsigned char f = 1;
+                if (prune) {
+                    const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
+                    const int rx1 = min(rx0 + RN_RW, p.W) - 1, ry1 = min(ry0 + RN_RH, p.H) - 1;
+                    float ub = 0.f;
+                    for (int j = 0; j < n_live; ++j)
+                        ub += fs.amp[j] * folded_bound(lut, p.n4, p.radius, rx0, rx1, fs.ix[j], p.W) *
+                              folded_bound(lut, p.n4, p.radius, ry0, ry1, fs.iy[j] & 0x3fff, p.H);
+                    f = (ub * 1.001f >= lower) ? 1 : 0;
+                }
+                flags[reg] = f;
+            }
+            group_sync<G>(group);
+        }
+
+        float scale = 1.f;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool store = (pass == n_pass - 1);
+            float vmax = -INFINITY;
+            for (int reg = gwarp; reg < n_regions; reg += G) {
+                if (!store && !flags[reg]) continue;
+                const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
+                float acc[8][8];
+                bool any;
+                if (FAST)
+                    any = accumulate_fast<WIDE>(p, fs, n_live, rx0, ry0, lane, acc);
+                else
+                    any = accumulate_slow(p, ss, n_live, rx0, ry0, lane, acc);
+                const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
+                if (!store) {
+                    if (!any) {  // no spot reaches the region: all its pixels are exactly 0
+                        vmax = fmaxf(vmax, 0.f);
+                        continue;
+                    }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int y = y0 + i;
-                    if (y >= p.H) continue;
+                    for (int i = 0; i < 8; ++i) {
+                        const bool yok = y0 + i < p.H;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int x = x0 + 32 * h;
-                        float4 v = make_float4(acc[i][4 * h] * scale, acc[i][4 * h + 1] * scale,
-                                               acc[i][4 * h + 2] * scale, acc[i][4 * h + 3] * scale);
-                        float *dst = img + (size_t)y * p.W + x;
-                        if (vec_ok && x + 3 < p.W) {
-                            __stcs(reinterpret_cast<float4 *>(dst), v);
-                        } else {
-                            if (x < p.W) dst[0] = v.x;
-                            if (x + 1 < p.W) dst[1] = v.y;
-                            if (x + 2 < p.W) dst[2] = v.z;
-                            if (x + 3 < p.W) dst[3] = v.w;
+                        for (int h = 0; h < 2; ++h) {
+                            if (VEC) {  // W % 4 == 0: a float4 group is entirely inside or outside the frame
+                                const float m4 = fmaxf(fmaxf(acc[i][4 * h], acc[i][4 * h + 1]),
+                                                       fmaxf(acc[i][4 * h + 2], acc[i][4 * h + 3]));
+                                if (yok && x0 + 32 * h < p.W) vmax = fmaxf(vmax, m4);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (yok && x0 + 32 * h + q < p.W) vmax = fmaxf(vmax, acc[i][4 * h + q]);
+                            }
+                        }
+                    }
+                } else {
+                    const float sc = any ? scale : 0.f;
+                    float *dst = img + (size_t)y0 * p.W + x0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool yok = y0 + i < p.H;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float *d = dst + (size_t)i * p.W + 32 * h;
+                            if (VEC) {
+                                if (yok && x0 + 32 * h < p.W)
+                                    __stcs(reinterpret_cast<float4 *>(d),
+                                           any ? make_float4(acc[i][4 * h] * sc, acc[i][4 * h + 1] * sc,
+                                                             acc[i][4 * h + 2] * sc, acc[i][4 * h + 3] * sc)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f));
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (yok && x0 + 32 * h + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
+                            }
                         }
                     }
                 }
             }
-        }
-        if (!store) {
-            vmax = warp_max(vmax);
-            if (lane == 0) s_wmax[warp] = vmax;
-            __syncthreads();
-            float m = s_wmax[0];
+            if (!store) {
+                vmax = warp_max(vmax);
+                if (G > 1) {
+                    if (lane == 0) s_wmax[warp] = vmax;
+                    group_sync<G>(group);
 #pragma unroll
-            for (int k = 1; k < RN_WARPS; ++k) m = fmaxf(m, s_wmax[k]);
-            scale = 1.f / m;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
+                    for (int k = 0; k < G; ++k) vmax = fmaxf(vmax, s_wmax[group * G + k]);
+                }
+                scale = 1.f / vmax;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
+            }
         }
+        group_sync<G>(group);  // the group's spot arrays are reused by its next template
     }
+}
+
+template <bool FAST, int G, bool WIDE, bool VEC>
+static int launch_render(const RenderParams &p, int group_bytes, size_t lut_bytes, cudaStream_t st) {
+    constexpr int NGROUPS = RN_WARPS / G;
+    const size_t smem = lut_bytes + (size_t)NGROUPS * group_bytes;
+    DS_REQUIRE(smem <= 200 * 1024, "ds_render: cap=%d / radius=%d need %zu bytes of shared memory", p.cap, p.radius,
+               smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(render_kernel<FAST, G, WIDE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FAST, G, WIDE, VEC>, RN_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int want = (p.n_tmpl + NGROUPS - 1) / NGROUPS;
+    const int grid = want < num_sms() * per_sm ? want : num_sms() * per_sm;
+    render_kernel<FAST, G, WIDE, VEC><<<grid, RN_THREADS, smem, st>>>(p, group_bytes);
+    return check_launch("ds_render");
 }
 
 }  // namespace ds
@@ -411,7 +557,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
                          double clip_threshold, int32_t normalize, float *images) {
     using namespace ds;
     DS_REQUIRE(n_tmpl >= 0 && cap > 0 && H > 0 && W > 0, "ds_render: bad sizes");
-    DS_REQUIRE(H <= 16384 && W <= 16384, "ds_render: image larger than 16384 px per side");
+    DS_REQUIRE(H < 16384 && W < 16384, "ds_render: image larger than 16383 px per side");
     DS_REQUIRE(calibration != 0.0, "ds_render: calibration cannot be zero");
     DS_REQUIRE(sigma > 0.0, "ds_render: sigma must be positive");
     DS_REQUIRE((reinterpret_cast<uintptr_t>(images) & 15) == 0, "ds_render: images must be 16-byte aligned");
@@ -429,12 +575,8 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.cx = cx;
     p.cy = cy;
     const double ang = in_plane_angle_deg * (3.141592653589793 / 180.0);
-    p.ca = cos(ang);
-    p.sa = sin(ang);
-    if (in_plane_angle_deg == 0.0) {
-        p.ca = 1.0;
-        p.sa = 0.0;
-    }
+    p.ca = (in_plane_angle_deg == 0.0) ? 1.0 : cos(ang);
+    p.sa = (in_plane_angle_deg == 0.0) ? 0.0 : sin(ang);
     p.mirror = mirrored ? -1.0 : 1.0;
     p.sigma = sigma;
     p.clip = clip_threshold;
@@ -444,33 +586,48 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.table_size = 0;
     p.n4 = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // vector stores need every row start 16-byte aligned
-    if ((W & 3) != 0) { /* scalar path inside the kernel */
-    }
+    size_t lut_bytes = 0;
+    int group_bytes;
+    const int n_regions = ((W + RN_RW - 1) / RN_RW) * ((H + RN_RH - 1) / RN_RH);
+    const bool wide = fast && (radius >= W || radius >= H);
     if (fast) {
-        DS_REQUIRE(radius >= 0 && radius <= 4096, "ds_render: radius out of range");
+        DS_REQUIRE(radius >= 0 && radius <= 2048, "ds_render: radius out of range");
         int ts = 64;
         while (ts < 2 * cap) ts <<= 1;
         p.table_size = ts;
-        p.n4 = ((2 * radius + 5) >> 2) + 2;
-        const size_t smem = fast_smem_bytes(cap, p.n4, ts);
-        DS_REQUIRE(smem <= 200 * 1024, "ds_render: cap=%d / radius=%d need %zu bytes of shared memory", cap, radius,
-                   smem);
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(render_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = smem;
-        }
-        render_kernel<true><<<n_tmpl, RN_THREADS, smem, st>>>(p);
+        p.n4 = (2 * radius + 9 + 3) / 4 + 2;
+        lut_bytes = (size_t)4 * p.n4 * 16;
+        group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16 + n_regions);
     } else {
-        const size_t smem = slow_smem_bytes(cap);
-        DS_REQUIRE(smem <= 200 * 1024, "ds_render: cap=%d needs %zu bytes of shared memory", cap, smem);
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            cudaFuncSetAttribute(render_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = smem;
-        }
-        render_kernel<false><<<n_tmpl, RN_THREADS, smem, st>>>(p);
+        group_bytes = (int)slow_smem_bytes(cap) + n_regions;
     }
-    return check_launch("ds_render");
+    group_bytes = (group_bytes + 15) & ~15;
+    // warps per template: four (two templates in flight per CTA, measured best on B200 for sparse and
+    // medium patterns), the whole CTA for dense ones.  DS_RENDER_GROUP overrides (tuning / tests).
+    int G = cap <= 512 ? 4 : 8;
+    if (const char *e = getenv("DS_RENDER_GROUP")) {
+        const int g = atoi(e);
+        if (g == 1 || g == 2 || g == 4 || g == 8) G = g;
+    }
+    while (G < 8 && lut_bytes + (size_t)(RN_WARPS / G) * group_bytes > 96 * 1024) G <<= 1;
+#define DS_RN(F, GG, WD, V) launch_render<F, GG, WD, V>(p, group_bytes, lut_bytes, st)
+    // rows that are not 16-byte aligned (W % 4 != 0) and kernels wider than the image take the
+    // general-purpose instantiations; the common case gets the lean ones
+    if ((W & 3) != 0) return fast ? (wide ? DS_RN(true, 8, true, false) : DS_RN(true, 8, false, false))
+                                  : DS_RN(false, 8, false, false);
+    if (wide) return DS_RN(true, 8, true, true);
+    if (fast) {
+        switch (G) {
+            case 1: return DS_RN(true, 1, false, true);
+            case 2: return DS_RN(true, 2, false, true);
+            case 4: return DS_RN(true, 4, false, true);
+            default: return DS_RN(true, 8, false, true);
+        }
+    } else {
+        switch (G) {
+            case 1: return DS_RN(false, 1, false, true);
+            default: return DS_RN(false, 8, false, true);
+        }
+    }
+#undef DS_RN
 }
