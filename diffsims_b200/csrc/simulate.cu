@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
             // ---- threshold: keep I > max(I) * min_intensity (simulation_generator.py:237), in place
             const int n_stored = min(w.n_out, p.cap);
             int n_keep = 0;
-            if (p.model == DS_SHAPE_NONE_RETURN_S) {
+            if (p.model == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0) {  // threshold disabled
                 n_keep = n_stored;
             } else {
                 const double cut = w.max_I * p.min_intensity;

@@ -110,7 +110,7 @@ def structure_factors(structure, g_indices, g_hkls_array, debye_waller_factors=N
     frac_d, occ_d, start_d, coef_d, dw_d = t(frac), t(occ), t(start), t(coeffs), t(dw)
     pre_d = None
     if prefactor is not None and not np.isscalar(prefactor):
-        pre_d = t(np.broadcast_to(np.asarray(prefactor, float), (n_g,)))
+        pre_d = t(np.array(np.broadcast_to(np.asarray(prefactor, float), (n_g,))))
     F = torch.empty((n_g, 2), dtype=torch.float64, device=dev) if want_F else None
     I = torch.empty((n_g,), dtype=torch.float64, device=dev) if want_I else None
     rc = _cabi.lib().ds_structure_factors(
