@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the kinematical template-simulation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A STEP builds one template library of B orientations per GPU for the BASELINE config-2 workload
+(Si diamond cubic, 200 kV, reciprocal_radius 1.0, max_excitation_error 0.01, lorentzian, lobato, direct
+beam, 256 x 256 px float32 templates, sigma 10, calibration rr/128, normalised):
+    K1 structure factors + table packing -> K2 simulate (all rotations) -> K3 rasterise (all templates).
+`value` is templates/s over all GPUs with the rotation list already in HBM; `e2e` is the same library
+built through the public host-buffer call (TemplateLibraryBuilder.run_host): pinned host quaternions in,
+pinned host images out, every copy inside the timed region.  Rotation lists shard across ranks (weak
+scaling: B per GPU) with no data-path collective.
+
+`--impl reference` times the float64 CPU oracle (the port of the reference's numpy path; the reference itself
+cannot be imported in this image) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "templates/sec (Si, 256x256 px)"
+UNIT = "templates/s"
+WORKLOAD = dict(
+    workload="Si Fd-3m a=5.431 8 atoms, 200 kV, reciprocal_radius=1.0, max_excitation_error=0.01, "
+             "lorentzian, lobato, direct beam, 256x256 float32 templates, sigma=10, calibration=1/128, "
+             "normalised; uniform random orientations (BASELINE configs[1], synthetic rotation grid)",
+    kv=200, rr=1.0, s_max=0.01, shape=(256, 256), sigma=10.0, calibration=1.0 / 128)
+
+
+def si_phase():
+    from diffsims_b200.crystal import Atom, Lattice, Phase, Structure
+    a = 5.431
+    latt = Lattice(a, a, a, 90, 90, 90)
+    atoms = []
+    for c in [[0, 0, 0], [0.5, 0, 0.5], [0, 0.5, 0.5], [0.5, 0.5, 0]]:
+        atoms.append(Atom("Si", c))
+        atoms.append(Atom("Si", [c[0] + 0.25, c[1] + 0.25, c[2] + 0.25]))
+    return Phase("Si", space_group=227, structure=Structure(atoms, latt))
+
+
+def random_quats(n, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[q[:, 0] < 0] *= -1
+    return q
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init():
+    from oracle import kinematical as K
+    phase = si_phase()
+    _CPU["K"] = K
+    _CPU["phase"] = phase
+    _CPU["gs"] = K.GSet(phase.structure, WORKLOAD["rr"], True)
+    _CPU["wl"] = K.get_electron_wavelength(WORKLOAD["kv"])
+
+
+def _cpu_templates(quats):
+    """Spot list + rendered template for each quaternion with the float64 oracle; returns a checksum."""
+    if not _CPU:
+        _cpu_init()
+    K = _CPU["K"]
+    acc = 0.0
+    for q in quats:
+        G = K.quat_to_matrix(q)  # passive matrix: rotated = g @ G
+        r = K.simulate_rotation(_CPU["phase"].structure, _CPU["gs"], G, _CPU["wl"], WORKLOAD["s_max"])
+        img = K.diffraction_pattern(r["xyz"], r["intensity"], WORKLOAD["shape"], sigma=WORKLOAD["sigma"],
+                                    calibration=WORKLOAD["calibration"])
+        acc += float(img[128, 128])
+    return acc
+
+
+def cpu_baseline_single_core(seconds=12.0):
+    _cpu_init()
+    q = random_quats(4096, 123)
+    _cpu_templates(q[:4])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and n < len(q):
+        _cpu_templates(q[n:n + 16])
+        n += 16
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit=UNIT, cores=1, kind="port",
+                sample=f"{n} templates of the same workload (spot list + 256x256 sigma=10 render), "
+                       f"float64 numpy oracle, 1 process, {dt:.1f} s")
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the CPU oracle on every host core; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 24
+    sample = cores * per_worker
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+        def step(seed):
+            q = random_quats(sample, seed)
+            chunks = [q[i * per_worker:(i + 1) * per_worker] for i in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_templates, chunks, chunksize=1)
+            return time.perf_counter() - t0
+        for w in range(args.warmup):
+            step(1000 + w)
+        times = [step(w) for w in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD["workload"], templates_per_step=sample,
+                            note="reference cannot be imported in this image (orix/diffpy absent); this is the "
+                                 "float64 numpy port pinned by the reference's fixtures"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{sample} templates per step ({per_worker} per process x {cores} processes)"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.stop, self.index = [], threading.Event(), index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                     "--format=csv,noheader,nounits", "-lms", "100"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        try:
+            for line in proc.stdout:
+                self.samples.append([f.strip() for f in line.split(",")])
+                if self.stop.is_set():
+                    break
+        finally:
+            proc.kill()
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        time.sleep(0.25)
+        self.stop.set()
+        self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32768, help="orientations per GPU per step")
+    ap.add_argument("--chunk", type=int, default=4096, help="e2e pipeline chunk (templates)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from diffsims_b200 import SimulationGenerator
+    from diffsims_b200.library import TemplateLibraryBuilder, gather_counts, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, (H, W) = args.batch, WORKLOAD["shape"]
+    # weak scaling: the global rotation list has world * B entries, rank r owns a contiguous slice
+    lo, hi = shard_bounds(world * B, rank, world)
+    quats_all = random_quats(world * B, 0) if world * B <= (1 << 22) else None
+    q_host = (quats_all[lo:hi] if quats_all is not None else random_quats(B, rank)).copy()
+    q_host[:, 1:] *= -1  # active quaternions (the reference rotates g by ~rotation)
+    q_dev = torch.as_tensor(q_host, device=dev)
+
+    gen = SimulationGenerator(WORKLOAD["kv"])
+    builder = TemplateLibraryBuilder(gen, si_phase(), reciprocal_radius=WORKLOAD["rr"],
+                                     max_excitation_error=WORKLOAD["s_max"], shape=(H, W), sigma=WORKLOAD["sigma"],
+                                     calibration=WORKLOAD["calibration"])
+    builder.prepare()
+    builder.calibrate_cap(q_dev)
+    images = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+
+    k3_events = []
+
+    def step(timed):
+        builder.prepare()                       # K1 + table packing
+        spots = builder.simulate(q_dev)         # K2
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        builder.render(spots, images)           # K3
+        if timed:
+            b.record()
+            k3_events.append((a, b))
+        return spots
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    builder.launches = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t0.record()
+        for _ in range(args.steps):
+            spots = step(True)
+        t1.record()
+        barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    launches = builder.launches
+    k3_ms = float(np.mean([a.elapsed_time(b) for a, b in k3_events]))
+    all_counts = gather_counts(spots.count)     # the single collective of a sharded build (not timed)
+    mean_spots = float(all_counts.float().mean().item())
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the host-buffer call -----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        q_pin = torch.as_tensor(q_host).pin_memory()
+        out_pin = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            h2d, d2h = builder.run_host(q_pin, out_pin, chunk=args.chunk)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(3, min(args.steps, 5))
+        e0.record()
+        for _ in range(n_e2e):
+            h2d, d2h = builder.run_host(q_pin, out_pin, chunk=args.chunk)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # correctness guard: the host images are the device images
+        assert torch.equal(out_pin[:64], images[:64].cpu()), "e2e images differ from the device-resident images"
+        e2e = dict(value=world * B * n_e2e / (float(te.item()) * 1e-3), unit=UNIT,
+                   h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
+                   api="TemplateLibraryBuilder.run_host (pinned host quaternions -> pinned host float32 images)")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    for cand in (ROOT / "MEASURED_PEAKS.json",):
+        if cand.exists():
+            peaks = json.loads(cand.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = B * H * W * 4
+    achieved = algo_bytes / (k3_ms * 1e-3) / 1e9
+    traffic = None
+    prof = ROOT / "profiles" / "k3_traffic.json"
+    if prof.exists():
+        try:
+            per_tmpl = json.loads(prof.read_text())["dram_bytes_per_template"]
+            traffic = per_tmpl * B
+        except Exception:
+            traffic = None
+    roofline = dict(kernel="render_kernel (K3)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+                    frac=achieved / peak, traffic=traffic, algorithmic_bytes_per_launch=algo_bytes,
+                    kernel_ms=k3_ms, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    share_of_step=k3_ms * args.steps / elapsed_ms)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single_core()
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64 (structure factors, excitation error, intensities) + f32 (raster)", data="synthetic",
+                config=dict(workload=WORKLOAD["workload"], templates_per_gpu_per_step=B, n_g=int(builder.gtable.n),
+                            mean_spots_per_template=mean_spots, spot_capacity=int(builder.cap),
+                            l2="each step writes %.1f GB of templates per GPU (>> 126 MB L2), so no input or "
+                               "output survives in L2 between steps" % (algo_bytes / 1e9),
+                            parallelism=f"rotation list sharded over {world} rank(s), no data-path collective"),
+                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks.summary())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
