@@ -42,6 +42,7 @@ struct RenderParams {
     int normalize;
     int table_size;  // fast: hash slots (power of two)
     int n4;          // fast: float4 entries per shifted LUT copy
+    int stage;       // 1: spot rows are prefetched into shared memory with cp.async.bulk (TMA engine)
     float *images;
 };
 
@@ -298,6 +299,16 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
     FastSmem fs;
     SlowSmem ss;
     unsigned char *flags;  // [n_regions] 1 = the region can hold the template maximum
+    // double-buffered staging of the next template's spot rows (xyz [cap][3] + intensity [cap], float64),
+    // filled by cp.async.bulk one template ahead: under a saturated write stream a dependent global load
+    // costs microseconds, which would otherwise serialise count -> spots -> pixels for every template
+    double *stage[2] = {nullptr, nullptr};
+    const int stage_elems = p.cap * 4;
+    if (p.stage) {
+        stage[0] = reinterpret_cast<double *>(gbase);
+        stage[1] = stage[0] + stage_elems;
+        gbase += (size_t)2 * stage_elems * sizeof(double);
+    }
     if (FAST) {
         fs = carve_fast(gbase, p);
         fs.lut = lut;
@@ -306,20 +317,52 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         ss = carve_slow(gbase, p);
         flags = reinterpret_cast<unsigned char *>(ss.yhi + p.cap);
     }
+    __shared__ __align__(8) uint64_t s_bar[NGROUPS][2];
+    if (p.stage) {
+        if (gtid == 0) {
+            mbar_init(&s_bar[group][0], 1);
+            mbar_init(&s_bar[group][1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    auto prefetch = [&](int t, int buf) {  // called by one thread of the group
+        const uint32_t bx = (uint32_t)p.cap * 24u, bi = (uint32_t)p.cap * 8u;
+        mbar_expect_tx(&s_bar[group][buf], bx + bi);
+        bulk_g2s(stage[buf], p.xyz + (size_t)t * p.cap * 3, bx, &s_bar[group][buf]);
+        bulk_g2s(stage[buf] + p.cap * 3, p.intensity + (size_t)t * p.cap, bi, &s_bar[group][buf]);
+    };
 
     const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
     const int n_regions = nrx * nry;
     const int lx = lane & 7, ly = lane >> 3;
 
-    for (int t = blockIdx.x * NGROUPS + group; t < p.n_tmpl; t += gridDim.x * NGROUPS) {
+    const int t_first = blockIdx.x * NGROUPS + group, t_stride = gridDim.x * NGROUPS;
+    int n_next = 0, iter = 0;
+    if (t_first < p.n_tmpl) {
+        n_next = p.count[t_first];
+        if (p.stage && gtid == 0) prefetch(t_first, 0);
+    }
+    for (int t = t_first; t < p.n_tmpl; t += t_stride, ++iter) {
         // ---- project spots to detector pixels (simulation2d.py:261-285, :422-430), float64 -----------
-        const int n = min(p.count[t], p.cap);
-        const size_t row = (size_t)t * p.cap;
+        const int n = min(n_next, p.cap);
+        const int buf = iter & 1;
+        if (t + t_stride < p.n_tmpl) {  // one template ahead: count in a register, spot rows by bulk copy
+            n_next = p.count[t + t_stride];
+            if (p.stage && gtid == 0) prefetch(t + t_stride, buf ^ 1);
+        }
+        const double *sxyz = p.xyz + (size_t)t * p.cap * 3;
+        const double *sint = p.intensity + (size_t)t * p.cap;
+        if (p.stage) {
+            mbar_wait(&s_bar[group][buf], (uint32_t)(iter >> 1) & 1u);
+            sxyz = stage[buf];
+            sint = stage[buf] + p.cap * 3;
+        }
         if (FAST) {
             for (int e = gtid; e < p.table_size; e += GT) fs.hash[e] = 0ull;
             group_sync<G>(group);
             for (int j = gtid; j < n; j += GT) {
-                const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
+                const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
                 // r cos(+-atan2(y, x) + a) + cx written without the polar round trip
                 const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
                 const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
@@ -344,7 +387,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                     }
                 }
                 fs.key[j] = key;
-                fs.inten[j] = (float)p.intensity[row + j];
+                fs.inten[j] = (float)sint[j];
             }
             group_sync<G>(group);
             if (gwarp == 0) {  // deterministic compaction of the surviving spots
@@ -381,10 +424,10 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                     bool live = false, inframe = false;
                     double px = 0, py = 0, I = 0, rad = 0;
                     if (j < n) {
-                        const double xs = p.xyz[3 * (row + j)] / p.cal, ys = p.xyz[3 * (row + j) + 1] / p.cal;
+                        const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
                         px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
                         py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
-                        I = p.intensity[row + j];
+                        I = sint[j];
                         if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
                             inframe = true;
                             rad = sqrt(log(p.clip / (pref * I)) / ef);  // detector_functions.py:339
@@ -601,10 +644,18 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     } else {
         group_bytes = (int)slow_smem_bytes(cap) + n_regions;
     }
+    // stage the spot rows through shared memory when they are small and 16-byte granular
+    p.stage = (cap <= 512 && (cap & 1) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(intensity) & 15) == 0)
+                  ? 1
+                  : 0;
+    if (getenv("DS_RENDER_NOSTAGE")) p.stage = 0;
+    if (p.stage) group_bytes += 2 * cap * 32;
     group_bytes = (group_bytes + 15) & ~15;
-    // warps per template: four (two templates in flight per CTA, measured best on B200 for sparse and
-    // medium patterns), the whole CTA for dense ones.  DS_RENDER_GROUP overrides (tuning / tests).
-    int G = cap <= 512 ? 4 : 8;
+    // warps per template: the whole CTA (G = 8) measured best on B200 once the spot rows are prefetched
+    // (one 256 KB template per CTA keeps the write stream of an SM inside two DRAM-page-friendly windows);
+    // DS_RENDER_GROUP overrides (tuning / tests).
+    int G = 8;
     if (const char *e = getenv("DS_RENDER_GROUP")) {
         const int g = atoi(e);
         if (g == 1 || g == 2 || g == 4 || g == 8) G = g;

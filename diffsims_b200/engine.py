@@ -92,32 +92,46 @@ def atom_arrays(structure, debye_waller_factors, scattering_params):
             np.asarray(coeffs, float).reshape(-1, 10), np.asarray(dw, float))
 
 
+class AtomTable:
+    """Device copy of a structure's atom arrays (grouped by element) for K1."""
+
+    def __init__(self, structure, debye_waller_factors, scattering_params, dev):
+        if scattering_params not in SCATTERING_IDS:
+            raise NotImplementedError(
+                "The scattering parameters `{}` are not implemented. "
+                "See documentation for available implementations.".format(scattering_params))
+        frac, occ, start, coeffs, dw = atom_arrays(structure, debye_waller_factors, scattering_params)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+        self.n_atoms, self.n_elem = frac.shape[0], coeffs.shape[0]
+        self.frac, self.occ, self.start, self.coeffs, self.dw = t(frac), t(occ), t(start), t(coeffs), t(dw)
+        self.model = SCATTERING_IDS[scattering_params]
+
+
+def launch_structure_factors(atoms: AtomTable, hkl_d, gnorm_d, prefactor_d=None, F=None, I=None):
+    """Enqueue K1 on the current stream (no host work, no synchronisation)."""
+    rc = _cabi.lib().ds_structure_factors(
+        _stream(), hkl_d.shape[0], _cabi.ptr(hkl_d), _cabi.ptr(gnorm_d), atoms.n_atoms, _cabi.ptr(atoms.frac),
+        _cabi.ptr(atoms.occ), atoms.n_elem, _cabi.ptr(atoms.start), _cabi.ptr(atoms.coeffs), _cabi.ptr(atoms.dw),
+        atoms.model, _cabi.ptr(prefactor_d), _cabi.ptr(F), _cabi.ptr(I))
+    _cabi.check(rc, "ds_structure_factors")
+
+
 def structure_factors(structure, g_indices, g_hkls_array, debye_waller_factors=None,
                       scattering_params="lobato", prefactor=None, dev=None, want_F=True, want_I=True):
     """K1 on device. Returns (F [n,2] float64 tensor or None, I [n] float64 tensor or None)."""
-    if scattering_params not in SCATTERING_IDS:
-        raise NotImplementedError(
-            "The scattering parameters `{}` are not implemented. "
-            "See documentation for available implementations.".format(scattering_params))
     dev = device(dev)
-    frac, occ, start, coeffs, dw = atom_arrays(structure, debye_waller_factors, scattering_params)
+    atoms = AtomTable(structure, debye_waller_factors, scattering_params, dev)
     hkl = torch.as_tensor(np.ascontiguousarray(np.asarray(g_indices, float).reshape(-1, 3)), device=dev)
     gn = torch.as_tensor(np.ascontiguousarray(np.asarray(g_hkls_array, float).reshape(-1)), device=dev)
     n_g = hkl.shape[0]
     if gn.shape[0] != n_g:
         raise ValueError("g_indices and g_hkls_array must have the same length")
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
-    frac_d, occ_d, start_d, coef_d, dw_d = t(frac), t(occ), t(start), t(coeffs), t(dw)
     pre_d = None
     if prefactor is not None and not np.isscalar(prefactor):
-        pre_d = t(np.array(np.broadcast_to(np.asarray(prefactor, float), (n_g,))))
+        pre_d = torch.as_tensor(np.array(np.broadcast_to(np.asarray(prefactor, float), (n_g,))), device=dev)
     F = torch.empty((n_g, 2), dtype=torch.float64, device=dev) if want_F else None
     I = torch.empty((n_g,), dtype=torch.float64, device=dev) if want_I else None
-    rc = _cabi.lib().ds_structure_factors(
-        _stream(), n_g, _cabi.ptr(hkl), _cabi.ptr(gn), frac.shape[0], _cabi.ptr(frac_d), _cabi.ptr(occ_d),
-        coeffs.shape[0], _cabi.ptr(start_d), _cabi.ptr(coef_d), _cabi.ptr(dw_d),
-        SCATTERING_IDS[scattering_params], _cabi.ptr(pre_d), _cabi.ptr(F), _cabi.ptr(I))
-    _cabi.check(rc, "ds_structure_factors")
+    launch_structure_factors(atoms, hkl, gn, pre_d, F, I)
     if I is not None and prefactor is not None and np.isscalar(prefactor) and prefactor != 1:
         I *= float(prefactor)
     return F, I
@@ -140,19 +154,36 @@ class GTable:
         return self.xyz.shape[0]
 
 
+class GTablePlan:
+    """Everything about a (structure, g set) that does not change between library builds: the enumerated
+    hkl / Cartesian g and the atom table, uploaded once.  ``run()`` enqueues K1 + the table packing on the
+    current stream and returns a fresh ``GTable`` -- no host arithmetic, no host<->device synchronisation."""
+
+    def __init__(self, structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):
+        dev = device(dev)
+        self.hkl = np.ascontiguousarray(hkl)
+        self.xyz_host = np.ascontiguousarray(np.asarray(xyz, float))
+        gnorm = np.sqrt((self.xyz_host ** 2).sum(axis=1))
+        self.g_max = float(gnorm.max()) if gnorm.size else 0.0
+        self.atoms = AtomTable(structure, debye_waller_factors, scattering_params, dev)
+        self.hkl_d = torch.as_tensor(self.hkl.astype(float), device=dev)
+        self.gnorm_d = torch.as_tensor(gnorm, device=dev)
+        self.xyz_d = torch.as_tensor(self.xyz_host, device=dev)
+
+    def run(self):
+        n = self.xyz_d.shape[0]
+        dev = self.xyz_d.device
+        I0 = torch.empty((n,), dtype=torch.float64, device=dev)
+        f32 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        if n:
+            launch_structure_factors(self.atoms, self.hkl_d, self.gnorm_d, None, None, I0)
+            _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), n, _cabi.ptr(self.xyz_d), _cabi.ptr(f32)),
+                        "ds_pack_gtable")
+        return GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max)
+
+
 def make_gtable(structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):
-    dev = device(dev)
-    hkl = np.ascontiguousarray(hkl)
-    xyz = np.ascontiguousarray(np.asarray(xyz, float))
-    gnorm = np.sqrt((xyz ** 2).sum(axis=1))
-    _, I0 = structure_factors(structure, hkl, gnorm, debye_waller_factors, scattering_params,
-                              dev=dev, want_F=False)
-    xyz_d = torch.as_tensor(xyz, device=dev)
-    f32 = torch.empty((xyz.shape[0], 4), dtype=torch.float32, device=dev)
-    _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), xyz.shape[0], _cabi.ptr(xyz_d), _cabi.ptr(f32)),
-                "ds_pack_gtable")
-    return GTable(hkl=hkl, xyz_host=xyz, xyz=xyz_d, f32=f32, I0=I0,
-                  g_max=float(gnorm.max()) if gnorm.size else 0.0)
+    return GTablePlan(structure, hkl, xyz, debye_waller_factors, scattering_params, dev).run()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -200,7 +231,7 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
         inten = torch.empty((n_rot, cap), dtype=torch.float64, device=dev)
         exc = torch.empty((n_rot, cap), dtype=torch.float64, device=dev) if want_exc else None
         max_count = torch.zeros((1,), dtype=torch.int32, device=dev)
-        if gt.n == 0:
+        if gt.n == 0 or n_rot == 0:
             count.zero_()
             return SpotTable(count, g_index, xyz, inten, exc, cap)
         rc = _cabi.lib().ds_simulate(

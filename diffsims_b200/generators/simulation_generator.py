@@ -86,8 +86,8 @@ class SimulationGenerator:
             return name, minima
         return None, minima
 
-    def _g_table(self, phase, reciprocal_radius, with_direct_beam, debye_waller_factors):
-        """Host enumeration (from_min_dspacing, reciprocal_lattice_vector.py:1077-1142) + K1."""
+    def _g_plan(self, phase, reciprocal_radius, with_direct_beam, debye_waller_factors):
+        """Host enumeration (from_min_dspacing, reciprocal_lattice_vector.py:1077-1142) + uploads."""
         lat = phase.structure.lattice
         hkl = g_set_from_min_dspacing(lat, 1 / reciprocal_radius, include_zero_vector=with_direct_beam)
         if with_direct_beam:
@@ -95,7 +95,11 @@ class SimulationGenerator:
             # (simulation_generator.py:351-353): the direct beam is listed twice, as in the reference
             hkl = np.vstack([hkl, np.zeros((1, 3), dtype=hkl.dtype)])
         xyz = hkl.astype(float) @ np.asarray(lat.recbase, dtype=float).T
-        return engine.make_gtable(phase.structure, hkl, xyz, debye_waller_factors, self.scattering_params)
+        return engine.GTablePlan(phase.structure, hkl, xyz, debye_waller_factors, self.scattering_params)
+
+    def _g_table(self, phase, reciprocal_radius, with_direct_beam, debye_waller_factors):
+        """Per-phase g table with structure factors (K1)."""
+        return self._g_plan(phase, reciprocal_radius, with_direct_beam, debye_waller_factors).run()
 
     def _simulate_phase(self, phase, rotation, reciprocal_radius, with_direct_beam, max_excitation_error,
                         shape_factor_width, debye_waller_factors):

@@ -64,11 +64,16 @@ class TemplateLibraryBuilder:
         self.prec = float(np.deg2rad(generator.precession_angle))
         self.cap = cap
         self.gtable = None
+        self.plan = None   # host enumeration + uploads of the phase, made once
         self.launches = 0  # kernels of libdiffsims_b200.so launched by this builder
 
     # -- K1 ----------------------------------------------------------------------------------------
     def prepare(self):
-        self.gtable = self.gen._g_table(self.phase, self.rr, self.with_direct_beam, self.dw)
+        """K1: structure factors of the phase's g set + the float4 table K2 stages (two launches, async).
+        The integer hkl enumeration and the atom table are a host-side plan built on first use."""
+        if self.plan is None:
+            self.plan = self.gen._g_plan(self.phase, self.rr, self.with_direct_beam, self.dw)
+        self.gtable = self.plan.run()
         self.launches += 2  # structure factors + table packing
         if self.cap is None:
             self.cap = engine.estimate_cap(self.gtable.n, self.gtable.g_max, self.s_max, self.prec)

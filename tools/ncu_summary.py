@@ -1,0 +1,54 @@
+"""Summarise an ncu report into profiles/<name>.md (per-launch key metrics).  Usage:
+    python tools/ncu_summary.py gpurun_out/prof_r01.ncu-rep profiles/r01_kernels.md
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_write.sum.per_second", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines = [f"# ncu --set full summary of `{rep}`", "",
+             "(`--clock-control none`; per-launch values; times under ncu are serialised/cold and are NOT bench numbers)", ""]
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        lines.append(f"## {name.split('(')[0]}  (launch id {r[idx['ID']]})")
+        lines.append("")
+        lines.append("| metric | value | unit |")
+        lines.append("|---|---|---|")
+        for k in KEYS:
+            if k in idx:
+                lines.append(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |")
+        lines.append("")
+    open(out, "w").write("\n".join(lines))
+    print(out)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
