@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
             group_sync<G>(group);
         }
 
-        float scale = 1.f;
+        float scale = 1.f, vmax_all = INFINITY;
         for (int pass = 0; pass < n_pass; ++pass) {
             const bool store = (pass == n_pass - 1);
             float vmax = -INFINITY;
@@ -534,7 +534,16 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                         }
                     }
                 } else {
-                    const float sc = any ? scale : 0.f;
+                    float sc = any ? scale : 0.f;
+                    // numpy divides: the maximum pixel is exactly 1.  acc * (1 / max) can be 1 ulp off, so the
+                    // (few) regions that can hold the maximum scale here and pin that pixel.
+                    if (n_pass == 2 && any && flags[reg]) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[i][j] = (acc[i][j] == vmax_all) ? 1.0f : acc[i][j] * sc;
+                        sc = 1.0f;
+                    }
                     float *dst = img + (size_t)y0 * p.W + x0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -566,6 +575,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                     for (int k = 0; k < G; ++k) vmax = fmaxf(vmax, s_wmax[group * G + k]);
                 }
                 scale = 1.f / vmax;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
+                vmax_all = vmax;
             }
         }
         group_sync<G>(group);  // the group's spot arrays are reused by its next template

@@ -1,0 +1,174 @@
+"""BASELINE.json configs at their full sizes, checked through size-independent properties, plus oracle
+spot checks on random samples (the oracle itself is far too slow for 1e5-1e6 templates)."""
+import numpy as np
+import pytest
+
+import diffsims_b200 as ds
+from diffsims_b200 import engine
+from diffsims_b200.library import TemplateLibraryBuilder, active_quaternions
+from oracle import kinematical as K
+from tests.golden import cases
+from tests.helpers import IMG_ATOL, compare_spots, random_quats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _deduped_intensity_sum(spots, shape, calibration, center):
+    """Per template: sum of the intensities that survive the in-frame test and last-write-wins (torch, f64)."""
+    import torch
+    H, W = shape
+    n, cap = spots.intensity.shape
+    valid = torch.arange(cap, device=spots.count.device)[None, :] < spots.count[:, None]
+    px = spots.xyz[..., 0] / calibration + center[0]
+    py = spots.xyz[..., 1] / calibration + center[1]
+    inframe = valid & (px >= 0) & (px < W) & (py >= 0) & (py < H)
+    key = torch.where(inframe, py.to(torch.int64) * W + px.to(torch.int64), torch.full_like(px, -1, dtype=torch.int64))
+    later_same = (key[:, :, None] == key[:, None, :]) & torch.triu(
+        torch.ones(cap, cap, dtype=torch.bool, device=key.device), diagonal=1)[None]
+    dead = later_same.any(dim=2)
+    live = inframe & ~dead
+    kept = torch.where(live, spots.intensity, torch.zeros_like(spots.intensity))   # padding is junk
+    return kept.sum(dim=1), kept.amax(dim=1)
+
+
+def _check_library(phase, kv, rr, s_max, n_rot, seed, shape=(256, 256), sigma=10.0, chunk=32768, dw=None,
+                   n_oracle=6):
+    import torch
+    gen = ds.SimulationGenerator(kv)
+    cal = rr / (shape[1] // 2)
+    b = TemplateLibraryBuilder(gen, phase, reciprocal_radius=rr, max_excitation_error=s_max, shape=shape,
+                               sigma=sigma, calibration=cal, debye_waller_factors=dw)
+    b.prepare()
+    dev = engine.device()
+    q_host = active_quaternions(random_quats(n_rot, seed))
+    center = (shape[1] // 2, shape[0] // 2)
+    img = torch.empty((min(chunk, n_rot), *shape), dtype=torch.float32, device=dev)
+    raw = torch.empty_like(img)
+    checksum = []
+    for lo in range(0, n_rot, chunk):
+        hi = min(lo + chunk, n_rot)
+        q = torch.as_tensor(q_host[lo:hi], device=dev)
+        b.calibrate_cap(q)
+        spots = b.simulate(q, check_overflow=True)
+        out = b.render(spots, img[: hi - lo])
+        # (1) determinism: a second pass is bit-identical
+        spots2 = b.simulate(q, check_overflow=True)
+        valid = torch.arange(spots.cap, device=dev)[None, :] < spots.count[:, None]
+        assert torch.equal(spots.count, spots2.count)
+        assert torch.equal(spots.intensity[valid], spots2.intensity[valid])   # (rows are padded with junk)
+        assert torch.equal(spots.xyz[valid], spots2.xyz[valid])
+        # (2) sortedness: reflections are listed in g-table order
+        gi = torch.where(valid, spots.g_index, torch.full_like(spots.g_index, 2 ** 30))
+        assert bool((gi[:, 1:] >= gi[:, :-1]).all())
+        # (3) every kept reflection passes the reference's threshold against its own pattern maximum
+        mx = torch.where(valid, spots.intensity, torch.zeros_like(spots.intensity)).amax(dim=1, keepdim=True)
+        assert bool((spots.intensity[valid] > (mx * gen.minimum_intensity).expand_as(spots.intensity)[valid]).all())
+        # (4) normalised templates peak at exactly 1 (or are all-zero when nothing is in frame)
+        peak = out.amax(dim=(1, 2))
+        tot, _ = _deduped_intensity_sum(spots, shape, cal, center)
+        assert bool(((peak == 1.0) | ((peak == 0.0) & (tot == 0.0))).all())
+        # (5) the integer rasteriser with reflect folding conserves intensity: sum(image) == sum(spots)
+        un = engine.render(spots.count, spots.xyz, spots.intensity, shape, sigma, cal, center, normalize=False,
+                           out=raw[: hi - lo])
+        s_img = un.sum(dim=(1, 2), dtype=torch.float64)
+        assert torch.allclose(s_img, tot, rtol=2e-5, atol=1e-30)
+        # (6) normalised = unnormalised / max, to float32 rounding
+        m = un.amax(dim=(1, 2), keepdim=True).clamp_min(1e-30)
+        assert float((out - un / m).abs().max()) <= 2e-6
+        checksum.append(float(s_img.sum()))
+        # (7) oracle spot check on a few templates of this chunk
+        if lo == 0:
+            gs = K.GSet(phase.structure, rr, True)
+            for r in np.random.default_rng(seed).choice(hi - lo, size=n_oracle, replace=False):
+                qa = q_host[lo + r]
+                G = K.quat_to_matrix(qa).T
+                ref = K.simulate_rotation(phase.structure, gs, G, gen.wavelength, s_max, debye_waller_factors=dw)
+                n = int(spots.count[r])
+                got = dict(g_index=spots.g_index[r, :n].cpu().numpy(), xyz=spots.xyz[r, :n].cpu().numpy(),
+                           intensity=spots.intensity[r, :n].cpu().numpy(), excitation_error=np.zeros(n))
+                compare_spots(ref, got, s_max=-1, rr=rr, prec=True)
+                ref_img = K.diffraction_pattern(ref["xyz"], ref["intensity"], shape, sigma=sigma, calibration=cal)
+                assert np.abs(out[r].cpu().numpy() - ref_img).max() <= IMG_ATOL
+    return checksum
+
+
+def test_config2_si_library_262144_orientations():
+    """BASELINE configs[1] at the >= 300k scale the north_star asks for (2^18 per GPU here)."""
+    _check_library(cases.phase("si"), 200, 1.0, 0.01, 1 << 18, seed=0)
+
+
+def test_config3_ti_hexagonal_300kv():
+    _check_library(cases.phase("ti"), 300, 1.0, 0.01, 16209, seed=1)   # size of the 0.5 deg 6/mmm grid
+
+
+def test_config5_multiphase_1M_orientations():
+    """Fe bcc + Fe fcc + Fe3C, ~333k orientations each (configs[4])."""
+    for name, seed in (("fe_bcc", 10), ("fe_fcc", 11), ("fe3c", 12)):
+        _check_library(cases.phase(name), 200, 1.0, 0.01, 333_334, seed=seed, n_oracle=3)
+
+
+def test_config4_large_cell_structure_factors():
+    """configs[3]: ~500 atoms / cell at reciprocal_radius 2.5 (N_g ~ 113k), K1 under load."""
+    import torch
+    phase = cases.phase("large")
+    gen = ds.SimulationGenerator(200)
+    plan = gen._g_plan(phase, 2.5, True, cases.DW)
+    gt = plan.run()
+    assert gt.n > 110_000
+    I0 = gt.I0.cpu().numpy()
+    # Friedel symmetry |F(g)|^2 == |F(-g)|^2 (real scattering factors): the table is listed in descending
+    # order, so row i and row n-3-i (ignoring the two trailing (000) rows) are Friedel mates
+    body = I0[:-2]
+    np.testing.assert_array_equal(plan.hkl[:-2], -plan.hkl[:-2][::-1])
+    np.testing.assert_allclose(body, body[::-1], rtol=1e-9, atol=1e-9 * body.max())
+    # F(000)^2 = (sum_j f_j(0) occ_j)^2
+    np.testing.assert_allclose(I0[-1], I0[-2])
+    idx = np.random.default_rng(0).choice(gt.n - 2, size=300, replace=False)
+    hkl = plan.hkl[idx]
+    ref = K.kinematical_intensities(phase.structure, hkl, phase.structure.lattice.rnorm(hkl), cases.DW)
+    np.testing.assert_allclose(I0[idx], ref, rtol=1e-8, atol=1e-10 * ref.max())
+    # and a few rotations through K2 with the streaming-tile path
+    q = active_quaternions(random_quats(4, 3))
+    spots = engine.simulate(gt, q, gen.wavelength, 0.01, 0.01, "lorentzian", want_exc=True)
+    gs = K.GSet(phase.structure, 2.5, True)
+    for r in range(2):
+        ref = K.simulate_rotation(phase.structure, gs, K.quat_to_matrix(q[r]).T, gen.wavelength, 0.01,
+                                  debye_waller_factors=cases.DW)
+        n = int(spots.count[r])
+        got = dict(g_index=spots.g_index[r, :n].cpu().numpy(), xyz=spots.xyz[r, :n].cpu().numpy(),
+                   intensity=spots.intensity[r, :n].cpu().numpy(),
+                   excitation_error=spots.exc[r, :n].cpu().numpy())
+        compare_spots(ref, got, s_max=0.01, rr=2.5)
+
+
+def test_render_linearity():
+    """Unnormalised rendering is linear in the spot list: image(A u B) = image(A) + image(B)."""
+    import torch
+    rng = np.random.default_rng(4)
+    dev = engine.device()
+    n, cap = 64, 64
+    xyz = np.zeros((n, cap, 3))
+    xyz[..., :2] = rng.uniform(-1.0, 1.0, (n, cap, 2))
+    inten = rng.uniform(0.1, 3.0, (n, cap))
+    cnt = np.full(n, cap, np.int32)
+    kw = dict(shape=(256, 256), sigma=6.0, calibration=1 / 128, center=(128, 128), normalize=False)
+    t = lambda a: torch.as_tensor(a, device=dev)
+    full = engine.render(t(cnt), t(xyz), t(inten), **kw)
+    a, b = inten.copy(), inten.copy()
+    a[:, cap // 2:] = 0
+    b[:, : cap // 2] = 0
+    part = engine.render(t(cnt), t(xyz), t(a), **kw) + engine.render(t(cnt), t(xyz), t(b), **kw)
+    # (zero-intensity spots still occupy their pixel, which is what makes the two halves comparable)
+    assert float((full - part).abs().max()) <= 1e-5 * float(full.max())
+    for fast in (True, False):  # homogeneity
+        kw2 = dict(kw, fast=fast, clip_threshold=1e-3)
+        one = engine.render(t(cnt), t(xyz), t(inten * 1000), **kw2)
+        two = engine.render(t(cnt), t(xyz), t(inten * 3000), **dict(kw2, clip_threshold=3e-3))
+        assert float((two - 3 * one).abs().max()) <= 1e-5 * float(two.max())
