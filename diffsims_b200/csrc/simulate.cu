@@ -35,6 +35,7 @@ struct SimParams {
     double s_max, width, minima, prec, min_intensity;
     float coarse_margin;
     int model;
+    int n_quad;  // > 0: average `model` over the precession circle with n_quad midpoint nodes on [0, pi]
     int *count;
     int *g_index;
     double *xyz;
@@ -86,9 +87,10 @@ struct WarpState {
 };
 
 // Refine up to 32 candidates (one per lane) in float64 and append the survivors to the output row.
-__device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot, bool have, int gi, int lane) {
+__device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot, bool have, int gi, int lane,
+                                       const double *__restrict__ s_cos) {
     bool keep = false;
-    double x = 0, y = 0, z = 0, s = 0, I = 0;
+    double x = 0, y = 0, z = 0, s = 0, I = 0, r_spot = 0;
     if (have) {
         const double gx = __ldg(p.g_xyz + 3 * (size_t)gi), gy = __ldg(p.g_xyz + 3 * (size_t)gi + 1),
                      gz = __ldg(p.g_xyz + 3 * (size_t)gi + 2);
@@ -96,7 +98,7 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
         y = w.m[3] * gx + w.m[4] * gy + w.m[5] * gz;
         z = w.m[6] * gx + w.m[7] * gy + w.m[8] * gz;
         // simulation_generator.py:355-360, evaluated as the reference writes it
-        const double r_spot = sqrt(x * x + y * y);
+        r_spot = sqrt(x * x + y * y);
         const double z_sphere = -sqrt(p.rs * p.rs - r_spot * r_spot) + p.rs;
         s = z_sphere - z;
         if (p.prec == 0.0) {
@@ -107,8 +109,28 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
             const double dn = P_z - sqrt(p.rs * p.rs - (r_spot - P_t) * (r_spot - P_t));
             keep = (z - p.s_max <= up) && (z + p.s_max >= dn);
         }
-        if (keep) I = shape_factor(p.model, s, p.width, p.minima, r_spot, p.prec) * __ldg(p.g_I0 + gi);
     }
+    double sf = 1.0;
+    if (p.n_quad > 0) {
+        // _shape_factor_precession (shape_factor_models.py:222-269): (1 / 2 pi) int_0^2pi f(s + r phi cos t) dt.
+        // The integrand is even and periodic in t, so the midpoint rule on [0, pi] (Gauss-Chebyshev in
+        // u = cos t) converges geometrically for the smooth models and as 1/n^2 for the kinked ones; the
+        // whole warp integrates one candidate at a time over a cosine table in shared memory.
+        for (int c = 0; c < 32; ++c) {
+            if (!__shfl_sync(0xffffffffu, (int)keep, c)) continue;
+            const double sc = __shfl_sync(0xffffffffu, s, c);
+            const double amp = __shfl_sync(0xffffffffu, r_spot, c) * p.prec;
+            double acc = 0.0;
+            for (int j = lane; j < p.n_quad; j += 32)
+                acc += shape_factor(p.model, sc + amp * s_cos[j], p.width, p.minima, 0.0, 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == c) sf = acc / (double)p.n_quad;
+        }
+    } else if (keep) {
+        sf = shape_factor(p.model, s, p.width, p.minima, r_spot, p.prec);
+    }
+    if (keep) I = sf * __ldg(p.g_I0 + gi);
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const int slot = w.n_out + __popc(mask & ((1u << lane) - 1u));
     if (keep && slot < p.cap) {
@@ -129,6 +151,8 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s_tile[2] = {reinterpret_cast<float4 *>(smem_raw),
                          reinterpret_cast<float4 *>(smem_raw) + (n_tiles > 1 ? tile_g : 0)};
+    double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1));
+    for (int j = threadIdx.x; j < p.n_quad; j += SIM_THREADS) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_list[SIM_WARPS][64];
 
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
                         n_list += __popc(mask);
                         __syncwarp();
                         if (n_list >= 32) {
-                            refine(p, w, rot, true, list[lane], lane);
+                            refine(p, w, rot, true, list[lane], lane, s_cos);
                             const int rest = n_list - 32;
                             const int carry = (lane < rest) ? list[32 + lane] : 0;
                             __syncwarp();
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
             if (n_tiles > 1) __syncthreads();  // everyone is done with `buf` before it is refilled
         }
         if (active) {
-            if (n_list > 0) refine(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane);
+            if (n_list > 0) refine(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
             __syncwarp();
             local_max_count = max(local_max_count, w.n_out);
             // ---- threshold: keep I > max(I) * min_intensity (simulation_generator.py:237), in place
@@ -355,10 +379,15 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
 
     const int n_tiles = (n_g <= SIM_RESIDENT_MAX_G) ? 1 : (n_g + SIM_TILE_G - 1) / SIM_TILE_G;
     const int tile_g = (n_tiles == 1) ? (n_g > 0 ? n_g : 1) : SIM_TILE_G;
-    const size_t smem = (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1);
+    // precession with a model other than the closed-form Lorentzian: numerical average over the circle
+    p.n_quad = 0;
+    if (precession_rad != 0.0 && shape_model != DS_SHAPE_LORENTZIAN_PRECESSION &&
+        shape_model != DS_SHAPE_NONE_RETURN_S && shape_model != DS_SHAPE_BINARY)
+        p.n_quad = (shape_model == DS_SHAPE_LORENTZIAN || shape_model == DS_SHAPE_ATANC) ? 2048 : 8192;
+    const size_t smem = (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1) + (size_t)p.n_quad * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(simulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16);
+        cudaFuncSetAttribute(simulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
         attr_set = true;
     }
     const int n_batches = (n_rot + SIM_WARPS - 1) / SIM_WARPS;

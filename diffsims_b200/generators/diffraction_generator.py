@@ -58,11 +58,8 @@ class DiffractionGenerator(object):
 
     def _native_model(self):
         minima = float(self.shape_factor_kwargs.get("minima_number", 5))
-        if self.precession_angle != 0:
-            if self.approximate_precession:
-                return "lorentzian_precession", minima
-            raise NotImplementedError(
-                "approximate_precession=False is not available on the device yet")
+        if self.precession_angle != 0 and self.approximate_precession:
+            return "lorentzian_precession", minima
         name = sfm.NATIVE.get(self.shape_factor_model)
         if name is None or not set(self.shape_factor_kwargs) <= {"minima_number"}:
             raise NotImplementedError(

@@ -75,15 +75,17 @@ class SimulationGenerator:
     def _native_model(self):
         """(native model name or None for a Python callable, minima_number)."""
         minima = float(self.shape_factor_kwargs.get("minima_number", 5))
-        if self.precession_angle != 0:
-            if self.approximate_precession:
-                return "lorentzian_precession", minima
-            raise NotImplementedError(
-                "approximate_precession=False (numerical integration of the rel-rod over the precession "
-                "circle) is not available on the device yet; use approximate_precession=True")
+        if self.precession_angle != 0 and self.approximate_precession:
+            return "lorentzian_precession", minima   # shape_factor_model is ignored, as in the reference
+        # precession_angle != 0 and not approximate: K2 averages the native model over the precession
+        # circle (_shape_factor_precession); a Python callable cannot be integrated in the kernel
         name = sfm.NATIVE.get(self.shape_factor_model)
         if name is not None and set(self.shape_factor_kwargs) <= {"minima_number"}:
             return name, minima
+        if self.precession_angle != 0:
+            raise NotImplementedError(
+                "approximate_precession=False needs a native shape factor model "
+                "(binary, linear, sinc, sin2c, atanc, lorentzian)")
         return None, minima
 
     def _g_plan(self, phase, reciprocal_radius, with_direct_beam, debye_waller_factors):

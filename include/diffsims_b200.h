@@ -87,6 +87,8 @@ int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz /*[n_g][3]*/, 
  *   g_lab = R(q) g,  R(q) the active rotation matrix of the unit quaternion q = (a, b, c, d)
  *   s     = (r_s - sqrt(r_s^2 - x^2 - y^2)) - z,   r_s = inv_wavelength
  *   keep  |s| < s_max (strict)           [precession: the two-surface test of :365-375]
+ *   precession_rad != 0 with DS_SHAPE_LORENTZIAN_PRECESSION uses the closed form (:183-219); with any other
+ *   model that model is averaged numerically over the precession circle (_shape_factor_precession, :222-269)
  *   I     = shape(s; width) * I0[g];     keep I > max_rot(I) * min_intensity   (min_intensity < 0: keep all)
  *
  * Output is padded per rotation: row r holds count[r] reflections in g-table order,

@@ -46,10 +46,42 @@ class TestDiffractionCalculator:
         gen = ds.SimulationGenerator(300, precession_angle=0.5, approximate_precession=True)
         assert gen.calculate_diffraction2d(make_phase(), reciprocal_radius=5.0).coordinates.size == 250
 
-    def test_precession_full_not_on_device_yet(self):
+    def test_precession_full(self):  # :154-161
         gen = ds.SimulationGenerator(300, precession_angle=0.5, approximate_precession=False)
+        assert gen.calculate_diffraction2d(make_phase(), reciprocal_radius=5.0).coordinates.size == 250
+
+    @pytest.mark.parametrize("model", ["lorentzian", "linear", "sinc", "sin2c", "atanc", sfm.binary])
+    def test_precession_full_matches_oracle_quad(self, model):
+        """K2's midpoint-rule average over the precession circle vs the reference's scipy.quad integral."""
+        phase = cases.phase("si")
+        gen = ds.SimulationGenerator(300, precession_angle=0.5, approximate_precession=False,
+                                     shape_factor_model=model)
+        rot = Rotation.from_euler([[0, 0, 0], [12, 34, 56]], degrees=True)
+        sim = gen.calculate_diffraction2d(phase, rot, reciprocal_radius=1.6, max_excitation_error=0.02)
+        gs = K.GSet(phase.structure, 1.6, True)
+        name = model if isinstance(model, str) else "binary"
+        # scipy.quad (the reference) hits its 50-subdivision limit on the kinked models and is then good to
+        # ~1e-4 only (its own error estimate); a converged midpoint rule is the tight check for those
+        quad_rtol = RTOL if name in ("lorentzian", "atanc", "binary") else 2e-3
+        for i, dv in enumerate(sim):
+            got = {tuple(h.astype(int)): v for h, v in zip(dv.hkl, dv.intensity)}
+            for converged, rtol in ((False, quad_rtol), (True, 2e-6)):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ref = K.simulate_rotation(phase.structure, gs, rot.to_matrix()[i], gen.wavelength, 0.02,
+                                              shape_factor_model=K.SHAPE_FACTOR_MODELS[name], precession_angle=0.5,
+                                              approximate_precession=False, converged_precession=converged)
+                big = ref["intensity"].max()
+                keep = ref["intensity"] > 1e-10 * big
+                assert dv.size >= keep.sum()
+                for h, v in zip(ref["hkl_int"][keep], ref["intensity"][keep]):
+                    assert abs(got[tuple(h)] - v) <= rtol * v + 1e-9 * big, (converged, h, got[tuple(h)], v)
+
+    def test_precession_full_needs_native_model(self):
+        gen = ds.SimulationGenerator(300, precession_angle=0.5, approximate_precession=False,
+                                     shape_factor_model=lambda s, w: s)
         with pytest.raises(NotImplementedError):
-            gen.calculate_diffraction2d(make_phase(), reciprocal_radius=5.0)
+            gen.calculate_diffraction2d(make_phase(), reciprocal_radius=1.0)
 
     def test_custom_shape_func(self):  # :163-168
         def local_excite(excitation_error, maximum_excitation_error, t):
