@@ -12,7 +12,7 @@ _lib = None
 
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_structure_factors", "ds_pack_gtable",
-           "ds_simulate", "ds_render")
+           "ds_simulate", "ds_render", "ds_polar_flatten")
 ABI_VERSION = 1
 
 
@@ -41,6 +41,7 @@ def lib():
     L.ds_pack_gtable.argtypes = [P, I, P, P]
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P]
+    L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
     for s in SYMBOLS[2:]:
         getattr(L, s).restype = c_int32
     _lib = L

@@ -1,0 +1,85 @@
+// polar_flatten_simulations on the packed result.
+//
+// Replaces the per-template Python loop of Simulation2D.polar_flatten_simulations
+// (diffsims/simulations/simulation2d.py:313-355): r = |g_xy|, theta = atan2(y, x)
+// (DiffractingVector.to_flat_polar, crystallography/_diffracting_vector.py:186-194), optional snapping to
+// radial / azimuthal axes with get_closest (simulation2d.py:767-781), removal of out-of-range spots, zero
+// padding to the longest template.  One warp per template, ballot compaction, float64 throughout.
+#include "common.cuh"
+
+namespace ds {
+
+// numpy.searchsorted(side="left") followed by the "previous entry is closer" correction of get_closest
+__device__ __forceinline__ int get_closest(const double *__restrict__ a, int n, double v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo;
+    const bool prev = (idx == n) || (fabs(v - a[max(idx - 1, 0)]) < fabs(v - a[min(idx, n - 1)]));
+    if (prev) idx -= 1;
+    return idx;
+}
+
+__global__ void polar_flatten_kernel(int n_tmpl, int cap, const int *__restrict__ count,
+                                     const double *__restrict__ xyz, const double *__restrict__ intensity,
+                                     int max_spots, int n_rad, const double *__restrict__ rad, int n_az,
+                                     const double *__restrict__ az, double *__restrict__ r_out,
+                                     double *__restrict__ t_out, double *__restrict__ i_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_tmpl) return;
+    const int n = min(count[warp], cap);
+    const size_t row = (size_t)warp * cap, orow = (size_t)warp * max_spots;
+    const bool snap = rad != nullptr && az != nullptr;
+    int n_out = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false;
+        double r = 0, t = 0, I = 0;
+        if (j < n) {
+            const double x = xyz[3 * (row + j)], y = xyz[3 * (row + j) + 1];
+            r = sqrt(x * x + y * y);
+            t = atan2(y, x);
+            I = intensity[row + j];
+            keep = true;
+            if (snap) {
+                const int ri = get_closest(rad, n_rad, r), ti = get_closest(az, n_az, t);
+                keep = (ri < n_rad - 1) && (ti < n_az - 1);
+                r = (double)ri;
+                t = (double)ti;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int d = n_out + __popc(mask & ((1u << lane) - 1u));
+        if (keep && d < max_spots) {
+            r_out[orow + d] = r;
+            t_out[orow + d] = t;
+            i_out[orow + d] = I;
+        }
+        n_out += __popc(mask);
+    }
+    for (int d = min(n_out, max_spots) + lane; d < max_spots; d += 32) {
+        r_out[orow + d] = 0.0;
+        t_out[orow + d] = 0.0;
+        i_out[orow + d] = 0.0;
+    }
+}
+
+}  // namespace ds
+
+extern "C" int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const double *xyz,
+                                const double *intensity, int32_t max_spots, int32_t n_radial,
+                                const double *radial_axes, int32_t n_azimuthal, const double *azimuthal_axes,
+                                double *r_out, double *theta_out, double *intensity_out) {
+    using namespace ds;
+    DS_REQUIRE(n_tmpl >= 0 && cap > 0 && max_spots >= 0, "ds_polar_flatten: bad sizes");
+    DS_REQUIRE((radial_axes == nullptr) == (azimuthal_axes == nullptr),
+               "ds_polar_flatten: radial and azimuthal axes must be given together");
+    if (n_tmpl == 0 || max_spots == 0) return 0;
+    const int threads = 256, warps = threads / 32;
+    polar_flatten_kernel<<<(n_tmpl + warps - 1) / warps, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_tmpl, cap, count, xyz, intensity, max_spots, n_radial, radial_axes, n_azimuthal, azimuthal_axes, r_out,
+        theta_out, intensity_out);
+    return check_launch("ds_polar_flatten");
+}

@@ -274,3 +274,26 @@ def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_an
         _cabi.ptr(out))
     _cabi.check(rc, "ds_render")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# polar flattening
+# ----------------------------------------------------------------------------------------------
+def polar_flatten(count, xyz, intensity, max_spots, radial_axes=None, azimuthal_axes=None):
+    """Device polar flattening of packed spot rows: returns (r, theta, intensity) float64 tensors
+    [n, max_spots] (r / theta hold axis indices when both axes are given)."""
+    dev = xyz.device
+    n, cap = intensity.shape
+    r = torch.empty((n, max_spots), dtype=torch.float64, device=dev)
+    t = torch.empty_like(r)
+    i = torch.empty_like(r)
+    rad = az = None
+    if radial_axes is not None and azimuthal_axes is not None:
+        rad = torch.as_tensor(np.ascontiguousarray(np.asarray(radial_axes, float)), device=dev)
+        az = torch.as_tensor(np.ascontiguousarray(np.asarray(azimuthal_axes, float)), device=dev)
+    rc = _cabi.lib().ds_polar_flatten(
+        _stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), _cabi.ptr(intensity), int(max_spots),
+        0 if rad is None else rad.numel(), _cabi.ptr(rad), 0 if az is None else az.numel(), _cabi.ptr(az),
+        _cabi.ptr(r), _cabi.ptr(t), _cabi.ptr(i))
+    _cabi.check(rc, "ds_polar_flatten")
+    return r, t, i

@@ -322,6 +322,16 @@ class Simulation2D:
 
     def polar_flatten_simulations(self, radial_axes=None, azimuthal_axes=None):
         """(n_simulations, max_spots) arrays of r, theta, intensity for template matching (:313-355)."""
+        packed = self._packed_phases()
+        if packed is not None and self.phase_index == 0 and self.rotation_index == 0:
+            # packed device result: one kernel per phase instead of a Python loop over templates
+            rows = [p.device_rows() for p in packed]
+            max_num_spots = max(int(c.max().item()) if c.numel() else 0 for c, _, _ in rows)
+            outs = [engine.polar_flatten(c, x, i, max_num_spots, radial_axes, azimuthal_axes) for c, x, i in rows]
+            r, t, inten = (torch.cat([o[k] for o in outs]).cpu().numpy() for k in range(3))
+            if radial_axes is not None and azimuthal_axes is not None:
+                r, t = r.astype(int), t.astype(int)
+            return r, t, inten
         flattened_vectors = [sim for sim in self]
         max_num_spots = max([v.size for v in flattened_vectors])
         r_templates = np.zeros((len(flattened_vectors), max_num_spots))
@@ -342,6 +352,15 @@ class Simulation2D:
             r_templates = np.array(r_templates, dtype=int)
             theta_templates = np.array(theta_templates, dtype=int)
         return r_templates, theta_templates, intensities_templates
+
+    def _packed_phases(self):
+        """The per-phase PackedVectors when the whole result is still packed on the device, else None."""
+        if isinstance(self.coordinates, PackedVectors):
+            return [self.coordinates]
+        if isinstance(self.coordinates, np.ndarray) and self.coordinates.dtype == object and len(self.coordinates) \
+                and all(isinstance(c, PackedVectors) for c in self.coordinates):
+            return list(self.coordinates)
+        return None
 
     # ------------------------------------------------------------------ rendering
     def get_diffraction_pattern(self, shape: Tuple[int, int] = None, sigma: float = 10,

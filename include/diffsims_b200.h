@@ -132,6 +132,21 @@ int ds_render(void *stream,
               double clip_threshold, int32_t normalize,
               float *images /*[n_tmpl][H][W]*/);
 
+/*
+ * Polar flattening of the packed result for template matching.
+ * Replaces Simulation2D.polar_flatten_simulations (diffsims/simulations/simulation2d.py:313-355) with
+ * DiffractingVector.to_flat_polar (diffsims/crystallography/_diffracting_vector.py:186-194) and get_closest
+ * (simulation2d.py:767-781): per template r = |g_xy|, theta = atan2(y, x), intensity, zero padded to
+ * max_spots.  With axes (both or neither) r and theta are replaced by the index of the closest axis entry
+ * and spots with r_idx >= n_radial - 1 or theta_idx >= n_azimuthal - 1 are dropped (then compacted).
+ * Outputs are float64 [n_tmpl][max_spots] (indices are stored as integral doubles).
+ */
+int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
+                     const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
+                     int32_t max_spots, int32_t n_radial, const double *radial_axes /*[n_radial] or NULL*/,
+                     int32_t n_azimuthal, const double *azimuthal_axes /*[n_azimuthal] or NULL*/,
+                     double *r_out, double *theta_out, double *intensity_out);
+
 #ifdef __cplusplus
 }
 #endif

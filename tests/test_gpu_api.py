@@ -387,3 +387,31 @@ def test_old_api_matches_reference_golden(golden_dir, cname):
             assert np.abs(img - e[f"{cname}_{i}_pattern"]).max() <= IMG_ATOL
     le = lib.get_library_entry(phase=cname, angle=c["eulers"][1])
     assert le["Sim"] is entry["simulations"][1]
+
+
+# ---------------------------------------------------------------- polar flattening on the packed result
+@pytest.mark.parametrize("axes", [False, True])
+def test_polar_flatten_packed_matches_object_path(axes):
+    """The device kernel (ds_polar_flatten) against the reference's per-template loop
+    (simulation2d.py:313-355), which still runs when the result is a plain list of DiffractingVectors."""
+    gen = ds.SimulationGenerator(200)
+    rots = [Rotation.random(9, rng=1), Rotation.random(5, rng=2)]
+    phases = [cases.phase("si"), cases.phase("ti")]
+    kw = {}
+    if axes:
+        kw = dict(radial_axes=np.linspace(0, 1.2, 40), azimuthal_axes=np.linspace(-np.pi, np.pi, 90))
+    for sim in (gen.calculate_diffraction2d(phases[0], rots[0], max_excitation_error=0.03),
+                gen.calculate_diffraction2d(phases, rots, max_excitation_error=0.03)):
+        fast = sim.polar_flatten_simulations(**kw)
+        # same data as plain objects -> the reference's loop
+        if sim.has_multiple_phases:
+            coords = [[c for c in pv] for pv in sim.coordinates]
+        else:
+            coords = [c for c in sim.coordinates]
+        plain = Simulation2D(phases=sim.phases, coordinates=coords, rotations=sim.rotations,
+                             simulation_generator=gen)
+        assert plain._packed_phases() is None
+        slow = plain.polar_flatten_simulations(**kw)
+        for a, b in zip(fast, slow):
+            assert a.shape == b.shape and a.dtype == b.dtype
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
