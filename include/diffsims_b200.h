@@ -147,6 +147,23 @@ int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *c
                      int32_t n_azimuthal, const double *azimuthal_axes /*[n_azimuthal] or NULL*/,
                      double *r_out, double *theta_out, double *intensity_out);
 
+/*
+ * Rotation-list producer: beam directions inside the stereographic triangle of a crystal system as Bunge
+ * Euler angles (0, Phi, phi2) in degrees and/or as the active quaternions ds_simulate consumes.
+ * Replaces get_beam_directions_grid (diffsims/generators/rotation_list_generators.py:176-267) for the cube
+ * meshes of get_cube_mesh_vertices (diffsims/generators/sphere_mesh_generators.py:96-197) with
+ * beam_directions_grid_to_euler (:486-526).  i_vals[n_i] is the 1-D face grid (device, computed by the host
+ * as the reference does: np.tan spacing per mesh type); mode 0 = no crop (triclinic), 1 = x >= epsilon
+ * (monoclinic as the reference evaluates it), 2 = the three plane tests n_k . v >= epsilon with
+ * normals_host[3][3] (HOST pointer).  Order-preserving compaction in two passes over
+ * ds_beam_grid_num_blocks(n_i) blocks: pass 0 fills block_counts, the caller exclusive-scans them into
+ * block_offsets (int64), pass 1 writes the survivors.  euler_deg / quat_active may be NULL.
+ */
+int64_t ds_beam_grid_num_blocks(int32_t n_i);
+int ds_beam_grid(void *stream, int32_t pass, int32_t n_i, const double *i_vals, int32_t mode,
+                 const double *normals_host /*[3][3] or NULL*/, double epsilon, int32_t *block_counts,
+                 const int64_t *block_offsets, double *euler_deg /*[n][3]*/, double *quat_active /*[n][4]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ own code, unmodified):
   ``calculate_ed_data``
 * ``matplotlib.pyplot``, ``PIL``, ``diffsims.utils.fourier_transform`` -> empty (plot/FFT
   helpers that the hot path never calls)
+* ``orix.sampling.sample_generators``, ``orix.quaternion.rotation`` -> empty names (imported by
+  rotation_list_generators.py but not used by ``get_beam_directions_grid``)
 
 Used only by tests/golden/make_golden.py.
 """
@@ -103,5 +105,18 @@ def load_reference():
                                       "diffsims/sims/diffraction_simulation.py")
     ns.diffraction_generator = _load("diffsims.generators.diffraction_generator",
                                      "diffsims/generators/diffraction_generator.py")
-    ns.sphere_mesh_generators = None
+    ns.sphere_mesh_generators = _load("diffsims.generators.sphere_mesh_generators",
+                                      "diffsims/generators/sphere_mesh_generators.py")
+    # rotation_list_generators imports two orix names at module level that get_beam_directions_grid never
+    # calls (get_sample_fundamental / get_sample_local / Rotation): empty placeholders
+    for n in ("orix", "orix.sampling", "orix.quaternion"):
+        _pkg(n)
+    sg = types.ModuleType("orix.sampling.sample_generators")
+    sg.get_sample_fundamental = sg.get_sample_local = None
+    sys.modules["orix.sampling.sample_generators"] = sg
+    rq = types.ModuleType("orix.quaternion.rotation")
+    rq.Rotation = None
+    sys.modules["orix.quaternion.rotation"] = rq
+    ns.rotation_list_generators = _load("diffsims.generators.rotation_list_generators",
+                                        "diffsims/generators/rotation_list_generators.py")
     return ns

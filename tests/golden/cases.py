@@ -121,3 +121,9 @@ ED_CASES = {
                            calibration=0.008, half_shape=(72, 72), shape=(144, 144), sigma=2,
                            eulers=random_eulers(4, 3)),
 }
+
+
+BEAM_GRID_SYSTEMS = ("cubic", "hexagonal", "trigonal", "tetragonal", "orthorhombic", "monoclinic", "triclinic")
+# diffsims/tests/generators/test_rotation_list_generator.py:80-94
+BEAM_GRID_SIZES_2DEG = dict(cubic=300, hexagonal=1050, trigonal=1657, tetragonal=852, orthorhombic=1657,
+                            monoclinic=6441, triclinic=12698)

@@ -13,6 +13,8 @@ Writes small ``.npz`` files next to this script.  Sources of truth:
                              sub-pixel branches) on seeded random spot lists.
 * ``sim_utils.npz``          reference ``utils/sim_utils.py`` ``get_kinematical_intensities``,
                              ``get_points_in_sphere`` on stand-in structures.
+* ``beam_grid.npz``          reference ``generators/rotation_list_generators.get_beam_directions_grid``
+                             (cube meshes) for the seven crystal systems.
 * ``ed_data.npz``            reference OLD api ``DiffractionGenerator.calculate_ed_data`` +
                              ``DiffractionSimulation.get_diffraction_pattern`` (run with the
                              euler2mat placeholder documented in _ref_loader.py).
@@ -111,6 +113,19 @@ for cname, c in cases.ED_CASES.items():
             out[f"{cname}_{i}_pattern"] = sim.get_diffraction_pattern(
                 shape=c["shape"], sigma=c["sigma"]).astype(np.float32)
 np.savez_compressed(HERE / "ed_data.npz", **out)
+
+# ---------------------------------------------------------------- rotation-list producers
+rlg = ns.rotation_list_generators
+out = {}
+for system in cases.BEAM_GRID_SYSTEMS:
+    g2 = rlg.get_beam_directions_grid(system, 2)
+    out[f"size_{system}_2deg"] = np.array(g2.shape[0])
+    if g2.shape[0] <= 2000:
+        out[f"edge_{system}_2deg"] = g2
+for system in ("cubic", "hexagonal", "monoclinic"):
+    for mesh in ("normalized_cube", "spherified_cube_corner", "spherified_cube_edge"):
+        out[f"{mesh}_{system}_5deg"] = rlg.get_beam_directions_grid(system, 5, mesh=mesh)
+np.savez_compressed(HERE / "beam_grid.npz", **out)
 
 for f in sorted(HERE.glob("*.npz")):
     print(f.name, f.stat().st_size)

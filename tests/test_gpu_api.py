@@ -415,3 +415,42 @@ def test_polar_flatten_packed_matches_object_path(axes):
         for a, b in zip(fast, slow):
             assert a.shape == b.shape and a.dtype == b.dtype
             np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------- rotation-list producers on the device
+def test_get_beam_directions_grid_matches_reference(golden_dir):
+    from diffsims_b200.generators.rotation_list_generators import (beam_directions_device,
+                                                                   get_beam_directions_grid,
+                                                                   get_grid_around_beam_direction)
+    gold = np.load(golden_dir / "beam_grid.npz")
+    for system in cases.BEAM_GRID_SYSTEMS:   # test_rotation_list_generator.py:80-94
+        grid = get_beam_directions_grid(system, 2)
+        assert grid.shape == (cases.BEAM_GRID_SIZES_2DEG[system], 3)
+        ref = K.beam_directions_grid(system, 2)
+        np.testing.assert_allclose(grid, ref, rtol=0, atol=1e-10)   # same points, same order
+    for key in gold.files:
+        if key.endswith("_5deg"):
+            mesh, system = key[:-5].rsplit("_", 1)
+            np.testing.assert_allclose(get_beam_directions_grid(system, 5, mesh=mesh), gold[key], atol=1e-10)
+    with pytest.raises(NotImplementedError):
+        get_beam_directions_grid("cubic", 10, mesh="invalid")
+    # the quaternions are the active form of Rotation.from_euler(grid)
+    euler, quat = beam_directions_device("cubic", 1.0)
+    ref_q = (~Rotation.from_euler(euler.cpu().numpy(), degrees=True)).data
+    np.testing.assert_allclose(quat.cpu().numpy(), ref_q, atol=1e-12)
+    # a >= 300k grid straight into HBM, usable by the simulate kernel
+    euler, quat = beam_directions_device("cubic", 0.058, want_euler=False)
+    assert euler is None and quat.shape[0] > 300_000
+    np.testing.assert_allclose(quat.norm(dim=1).cpu().numpy(), 1.0, atol=1e-12)
+    gen = ds.SimulationGenerator(200)
+    gt = gen._g_table(cases.phase("si"), 1.0, True, {})
+    spots = engine_simulate(gt, quat[:4096], gen)
+    assert int(spots.count.min()) >= 2   # at least the (doubled) direct beam everywhere
+    g = get_grid_around_beam_direction((0, 45, 30), 5)
+    assert len(g) == 72 and all(len(t) == 3 for t in g)
+    np.testing.assert_allclose([t[1] for t in g], 45.0, atol=1e-2)
+
+
+def engine_simulate(gt, quat, gen):
+    from diffsims_b200 import engine
+    return engine.simulate(gt, quat, gen.wavelength, 0.01, 0.01, "lorentzian")

@@ -176,3 +176,18 @@ def test_old_api_against_reference(g, cname):
             img = K.old_diffraction_pattern(r["coordinates"][m], r["intensities"][m], c["calibration"],
                                             c["shape"], c["sigma"])
             np.testing.assert_allclose(img, e[f"{cname}_{i}_pattern"], atol=2e-7)
+
+
+def test_beam_directions_grid_against_reference(golden_dir):
+    """Rotation-list producer: sizes pinned by the reference's tests
+    (tests/generators/test_rotation_list_generator.py:80-94) and full arrays from the reference itself."""
+    gold = np.load(golden_dir / "beam_grid.npz")
+    for system in cases.BEAM_GRID_SYSTEMS:
+        got = K.beam_directions_grid(system, 2)
+        assert got.shape[0] == cases.BEAM_GRID_SIZES_2DEG[system] == int(gold[f"size_{system}_2deg"])
+        if f"edge_{system}_2deg" in gold.files:
+            np.testing.assert_array_equal(got, gold[f"edge_{system}_2deg"])
+    for key in gold.files:
+        if key.endswith("_5deg"):
+            mesh, system = key[:-5].rsplit("_", 1)
+            np.testing.assert_array_equal(K.beam_directions_grid(system, 5, mesh=mesh), gold[key])
