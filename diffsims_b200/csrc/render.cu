@@ -54,9 +54,13 @@ struct FastSmem {
     unsigned long long *hash;  // [table_size]
     int *key;                  // [cap]   pixel key of spot j or -1
     float *inten;              // [cap]
-    short *ix, *iy;            // [cap]   compacted live spots
-    float *amp;                // [cap]
+    uint2 *spot;               // [cap]   compacted live spots: .x = ix | (iy | fold << 14) << 16, .y = amplitude bits
 };
+
+__device__ __forceinline__ int spot_ix(uint2 r) { return (int)(r.x & 0xffffu); }
+__device__ __forceinline__ int spot_iy(uint2 r) { return (int)((r.x >> 16) & 0x3fffu); }
+__device__ __forceinline__ bool spot_fold(uint2 r) { return (r.x >> 30) & 1u; }
+__device__ __forceinline__ float spot_amp(uint2 r) { return __uint_as_float(r.y); }
 
 __device__ __forceinline__ FastSmem carve_fast(unsigned char *base, const RenderParams &p) {
     FastSmem s;
@@ -67,11 +71,7 @@ __device__ __forceinline__ FastSmem carve_fast(unsigned char *base, const Render
     base += (size_t)p.cap * 4;
     s.inten = reinterpret_cast<float *>(base);
     base += (size_t)p.cap * 4;
-    s.amp = reinterpret_cast<float *>(base);
-    base += (size_t)p.cap * 4;
-    s.ix = reinterpret_cast<short *>(base);
-    base += (size_t)p.cap * 2;
-    s.iy = reinterpret_cast<short *>(base);
+    s.spot = reinterpret_cast<uint2 *>(base);
     return s;
 }
 
@@ -126,20 +126,58 @@ __device__ __forceinline__ void fma_tile(float (&acc)[8][8], const float (&wy)[8
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wy[i], wx[j], acc[i][j]);
 }
 
+// ---- hot path helpers: 32-bit shared-window addresses and explicit ld.shared (the generic-pointer form
+// costs an S2R + LEA address conversion per access) ------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+struct LutRef {
+    uint32_t base;  // shared address of copy 0
+    int n4, last;   // entries per copy, n4 - 1
+    int bias;       // R + 8
+};
+// taps L[a .. a+3] with a = offset + R + 8 already applied
+__device__ __forceinline__ float4 fetch4s(const LutRef &L, int a) {
+    const int i = min(max(a >> 2, 0), L.last);
+    return lds128(L.base + (uint32_t)(((a & 3) * L.n4 + i) << 4));
+}
+__device__ __forceinline__ float4 folded4s(const LutRef &L, int p0b /* p0 + R + 8 */, int c, int n, int R) {
+    float4 w = fetch4s(L, p0b - c);
+    if (c < R) w = add4(w, fetch4s(L, p0b + c + 1));               // image at -c - 1
+    if (c >= n - R) w = add4(w, fetch4s(L, p0b + c + 1 - 2 * n));  // image at 2n - 1 - c
+    return w;
+}
+
 // One warp region (64 x 32 px at rx0, ry0): accumulate all live spots into the lane's 8 x 8 tile.
-// Returns false (acc untouched) when no spot reaches the region.
+// Returns false (acc untouched) when no spot reaches the region.  The two 32-px column groups of the
+// region are culled separately (a spot's box is 2R+1 wide, the region 64).
 template <bool WIDE>
 __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const FastSmem &s, int n_live, int rx0,
                                                 int ry0, int lane, float (&acc)[8][8]) {
     const int lx = lane & 7, ly = lane >> 3;
     const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
     const int R = p.radius;
+    LutRef L;
+    L.base = smem_u32(s.lut);
+    L.n4 = p.n4;
+    L.last = p.n4 - 1;
+    L.bias = R + 8;
+    const uint32_t spot_s = smem_u32(s.spot);
+    const int xb = x0 + L.bias, yb = y0 + L.bias;
     bool any = false;
     for (int base = 0; base < n_live; base += 32) {
         const int j = base + lane;
         bool hit = false;
         if (j < n_live) {
-            const int sx = s.ix[j], sy = s.iy[j] & 0x3fff;
+            const uint2 r = lds64(spot_s + 8u * j);
+            const int sx = spot_ix(r), sy = spot_iy(r);
             hit = WIDE || (sx + R >= rx0 && sx - R < rx0 + RN_RW && sy + R >= ry0 && sy - R < ry0 + RN_RH);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -153,30 +191,40 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int sx = s.ix[base + b], syf = s.iy[base + b];
-            const int sy = syf & 0x3fff;
-            const float a = s.amp[base + b];
-            float4 xa, xb, ya, yb;
+            const uint2 r = lds64(spot_s + 8u * (base + b));
+            const int sx = spot_ix(r), sy = spot_iy(r);
+            const float a = spot_amp(r);
+            float4 ya, yb4;
             if (WIDE) {
-                xa = folded4<true>(s.lut, p.n4, R, x0, sx, p.W);
-                xb = folded4<true>(s.lut, p.n4, R, x0 + 32, sx, p.W);
                 ya = folded4<true>(s.lut, p.n4, R, y0, sy, p.H);
-                yb = folded4<true>(s.lut, p.n4, R, y0 + 4, sy, p.H);
+                yb4 = folded4<true>(s.lut, p.n4, R, y0 + 4, sy, p.H);
+            } else if (spot_fold(r)) {  // the box crosses a border: add the reflect-folded images
+                ya = folded4s(L, yb, sy, p.H, R);
+                yb4 = folded4s(L, yb + 4, sy, p.H, R);
             } else {
-                xa = fetch4(s.lut, p.n4, R, x0 - sx);
-                xb = fetch4(s.lut, p.n4, R, x0 + 32 - sx);
-                ya = fetch4(s.lut, p.n4, R, y0 - sy);
-                yb = fetch4(s.lut, p.n4, R, y0 + 4 - sy);
-                if (syf & 0x4000) {  // the box crosses a border: add the reflect-folded images
-                    xa = folded4<false>(s.lut, p.n4, R, x0, sx, p.W);
-                    xb = folded4<false>(s.lut, p.n4, R, x0 + 32, sx, p.W);
-                    ya = folded4<false>(s.lut, p.n4, R, y0, sy, p.H);
-                    yb = folded4<false>(s.lut, p.n4, R, y0 + 4, sy, p.H);
+                ya = fetch4s(L, yb - sy);
+                yb4 = fetch4s(L, yb + 4 - sy);
+            }
+            const float wy[8] = {a * ya.x, a * ya.y, a * ya.z, a * ya.w, a * yb4.x, a * yb4.y, a * yb4.z, a * yb4.w};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // column group h covers x in [rx0 + 32 h, rx0 + 32 h + 31]
+                if (!WIDE && !(sx + R >= rx0 + 32 * h && sx - R < rx0 + 32 * h + 32)) continue;
+                float4 xw;
+                if (WIDE)
+                    xw = folded4<true>(s.lut, p.n4, R, x0 + 32 * h, sx, p.W);
+                else if (spot_fold(r))
+                    xw = folded4s(L, xb + 32 * h, sx, p.W, R);
+                else
+                    xw = fetch4s(L, xb + 32 * h - sx);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i][4 * h + 0] = fmaf(wy[i], xw.x, acc[i][4 * h + 0]);
+                    acc[i][4 * h + 1] = fmaf(wy[i], xw.y, acc[i][4 * h + 1]);
+                    acc[i][4 * h + 2] = fmaf(wy[i], xw.z, acc[i][4 * h + 2]);
+                    acc[i][4 * h + 3] = fmaf(wy[i], xw.w, acc[i][4 * h + 3]);
                 }
             }
-            const float wx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            const float wy[8] = {a * ya.x, a * ya.y, a * ya.z, a * ya.w, a * yb.x, a * yb.y, a * yb.z, a * yb.w};
-            fma_tile(acc, wy, wx);
         }
     }
     return any;
@@ -296,9 +344,12 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         }
         __syncthreads();
     }
+    const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
+    const int n_regions = nrx * nry;
     FastSmem fs;
     SlowSmem ss;
     unsigned char *flags;  // [n_regions] 1 = the region can hold the template maximum
+    float *ubound;         // [G][n_regions] partial upper bounds
     // double-buffered staging of the next template's spot rows (xyz [cap][3] + intensity [cap], float64),
     // filled by cp.async.bulk one template ahead: under a saturated write stream a dependent global load
     // costs microseconds, which would otherwise serialise count -> spots -> pixels for every template
@@ -312,10 +363,12 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
     if (FAST) {
         fs = carve_fast(gbase, p);
         fs.lut = lut;
-        flags = reinterpret_cast<unsigned char *>(fs.iy + p.cap);
+        flags = reinterpret_cast<unsigned char *>(fs.spot + p.cap);
+        ubound = reinterpret_cast<float *>(flags + ((n_regions + 3) & ~3));
     } else {
         ss = carve_slow(gbase, p);
         flags = reinterpret_cast<unsigned char *>(ss.yhi + p.cap);
+        ubound = reinterpret_cast<float *>(flags + ((n_regions + 3) & ~3));
     }
     __shared__ __align__(8) uint64_t s_bar[NGROUPS][2];
     if (p.stage) {
@@ -333,8 +386,6 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         bulk_g2s(stage[buf] + p.cap * 3, p.intensity + (size_t)t * p.cap, bi, &s_bar[group][buf]);
     };
 
-    const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
-    const int n_regions = nrx * nry;
     const int lx = lane & 7, ly = lane >> 3;
 
     const int t_first = blockIdx.x * NGROUPS + group, t_stride = gridDim.x * NGROUPS;
@@ -406,9 +457,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                         const int d = n_live + __popc(mask & ((1u << lane) - 1u));
                         const int sx = key % p.W, sy = key / p.W;
                         const bool fold = sx < p.radius || sx >= p.W - p.radius || sy < p.radius || sy >= p.H - p.radius;
-                        fs.ix[d] = (short)sx;
-                        fs.iy[d] = (short)(sy | (fold ? 0x4000 : 0));
-                        fs.amp[d] = fs.inten[j];
+                        fs.spot[d] = make_uint2((unsigned)sx | ((unsigned)(sy | (fold ? 0x4000 : 0)) << 16),
+                                                __float_as_uint(fs.inten[j]));
                     }
                     n_live += __popc(mask);
                 }
@@ -473,8 +523,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
             if (prune) {
                 float amin = INFINITY, amax = -INFINITY;
                 for (int j = lane; j < n_live; j += 32) {
-                    amin = fminf(amin, fs.amp[j]);
-                    amax = fmaxf(amax, fs.amp[j]);
+                    amin = fminf(amin, spot_amp(fs.spot[j]));
+                    amax = fmaxf(amax, spot_amp(fs.spot[j]));
                 }
                 amin = -warp_max(-amin);
                 amax = warp_max(amax);
@@ -482,18 +532,28 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                 lower = amax * w0 * w0;
                 prune = amin >= 0.f && lower > 0.f;  // (NaN amplitudes fail both tests)
             }
-            for (int reg = gtid; reg < n_regions; reg += GT) {
-                unsigned char f = 1;
-                if (prune) {
+            // every warp of the group sums the bound over its share of the spots (lane = region), the partial
+            // sums meet in shared memory in a fixed order
+            for (int reg0 = 0; reg0 < n_regions; reg0 += 32) {
+                const int reg = reg0 + lane;
+                float ub = 0.f;
+                if (prune && reg < n_regions) {
                     const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                     const int rx1 = min(rx0 + RN_RW, p.W) - 1, ry1 = min(ry0 + RN_RH, p.H) - 1;
-                    float ub = 0.f;
-                    for (int j = 0; j < n_live; ++j)
-                        ub += fs.amp[j] * folded_bound(lut, p.n4, p.radius, rx0, rx1, fs.ix[j], p.W) *
-                              folded_bound(lut, p.n4, p.radius, ry0, ry1, fs.iy[j] & 0x3fff, p.H);
-                    f = (ub * 1.001f >= lower) ? 1 : 0;
+                    for (int j = gwarp; j < n_live; j += G) {
+                        const uint2 r = fs.spot[j];
+                        ub += spot_amp(r) * folded_bound(lut, p.n4, p.radius, rx0, rx1, spot_ix(r), p.W) *
+                              folded_bound(lut, p.n4, p.radius, ry0, ry1, spot_iy(r), p.H);
+                    }
                 }
-                flags[reg] = f;
+                if (reg < n_regions) ubound[gwarp * n_regions + reg] = ub;
+            }
+            group_sync<G>(group);
+            for (int reg = gtid; reg < n_regions; reg += GT) {
+                float ub = 0.f;
+#pragma unroll
+                for (int k = 0; k < G; ++k) ub += ubound[k * n_regions + reg];
+                flags[reg] = (!prune || ub * 1.001f >= lower) ? 1 : 0;
             }
             group_sync<G>(group);
         }
@@ -650,9 +710,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         p.table_size = ts;
         p.n4 = (2 * radius + 9 + 3) / 4 + 2;
         lut_bytes = (size_t)4 * p.n4 * 16;
-        group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16 + n_regions);
+        group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16);
     } else {
-        group_bytes = (int)slow_smem_bytes(cap) + n_regions;
+        group_bytes = (int)slow_smem_bytes(cap);
     }
     // stage the spot rows through shared memory when they are small and 16-byte granular
     p.stage = (cap <= 512 && (cap & 1) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15) == 0 &&
@@ -661,16 +721,19 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
                   : 0;
     if (getenv("DS_RENDER_NOSTAGE")) p.stage = 0;
     if (p.stage) group_bytes += 2 * cap * 32;
-    group_bytes = (group_bytes + 15) & ~15;
-    // warps per template: the whole CTA (G = 8) measured best on B200 once the spot rows are prefetched
-    // (one 256 KB template per CTA keeps the write stream of an SM inside two DRAM-page-friendly windows);
-    // DS_RENDER_GROUP overrides (tuning / tests).
-    int G = 8;
+    const int group_fixed = (group_bytes + 15) & ~15;  // + flags and per-warp bound partials, which depend on G
+    // warps per template, measured on B200 (tools/bench_configs.py): sparse patterns (<= 32 reflections) are
+    // write-bound and like the whole CTA on one template (one 256 KB window per CTA); denser ones are
+    // phase/latency-bound and like more templates in flight per SM.  DS_RENDER_GROUP overrides.
+    int G = cap <= 32 ? 8 : (cap <= 64 ? 4 : 2);
     if (const char *e = getenv("DS_RENDER_GROUP")) {
         const int g = atoi(e);
         if (g == 1 || g == 2 || g == 4 || g == 8) G = g;
     }
-    while (G < 8 && lut_bytes + (size_t)(RN_WARPS / G) * group_bytes > 96 * 1024) G <<= 1;
+    auto bytes_for = [&](int g) { return (group_fixed + ((n_regions + 3) & ~3) + g * n_regions * 4 + 15) & ~15; };
+    while (G < 8 && lut_bytes + (size_t)(RN_WARPS / G) * bytes_for(G) > 96 * 1024) G <<= 1;
+    if (wide || (W & 3) != 0) G = 8;
+    group_bytes = bytes_for(G);
 #define DS_RN(F, GG, WD, V) launch_render<F, GG, WD, V>(p, group_bytes, lut_bytes, st)
     // rows that are not 16-byte aligned (W % 4 != 0) and kernels wider than the image take the
     // general-purpose instantiations; the common case gets the lean ones
