@@ -9,8 +9,10 @@
 //
 // Mapping: one warp per rotation, persistent CTAs of 8 warps.  The per-phase g table (float4 rows
 // gx, gy, gz, |g|^2) is staged into shared memory with cp.async.bulk (TMA engine) -- once per CTA when it
-// fits, double-buffered tiles otherwise.  Each lane tests one g per step in float32 with a safety margin
-// (only z' = R[2,:].g is needed because rotation preserves |g|); a warp ballot + prefix sum compacts the
+// fits, double-buffered tiles otherwise.  Each lane tests four g per step in float32 with a safety margin
+// (only z' = R[2,:].g is needed because rotation preserves |g|; the Ewald test |s| < t is evaluated in the
+// cancellation-free, sqrt-free form f(z'+t) < 0 < f(z'-t), f(u) = r^2 + u (u - 2 r_s)); a warp ballot +
+// prefix sum compacts the
 // candidates into a per-warp list, and full warps of candidates are then refined in float64 (full rotation,
 // the reference's own excitation-error expression, strict cut, shape factor).  float64 is required for the
 // refine: the Lorentzian's sensitivity dI/I ~ 180 ds near s_max needs ds < 5e-8.
@@ -77,6 +79,16 @@ __device__ __forceinline__ double shape_factor(int model, double s, double w, do
         default:  // binary, return-s
             return 1.0;
     }
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    // volatile: the tile buffers are refilled by the async proxy between tiles
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 struct WarpState {
@@ -178,9 +190,11 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
         mbar_wait(&s_bar[0], 0);
     }
 
-    const float rs = (float)p.rs;
+    const float two_rs = 2.0f * (float)p.rs;
     const float thr = (float)p.s_max + p.coarse_margin;
+    const bool prec_on = p.prec != 0.0;
     const float P_z = (float)(p.rs * cos(p.prec)), P_t = (float)(p.rs * sin(p.prec));
+    const uint32_t tile_base_s = smem_u32(smem_raw);
     int local_max_count = 0;
 
     const int n_batches = (p.n_rot + SIM_WARPS - 1) / SIM_WARPS;
@@ -209,6 +223,7 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
         }
         int n_list = 0;
         int *list = s_list[warp];
+        const uint32_t list_s = smem_u32(list);
 
         if (n_tiles > 1) issue(0, 0);
         for (int t = 0; t < n_tiles; ++t) {
@@ -219,30 +234,44 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
                 phase[buf] ^= 1;
             }
             const int n = min(tile_g, p.n_g - t * tile_g);
-            const float4 *sg = s_tile[buf];
+            const uint32_t tile_s = tile_base_s + (buf ? (uint32_t)tile_g * 16u : 0u);
             if (active) {
-                for (int i0 = 0; i0 < n; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool cand = false;
-                    if (i < n) {
-                        const float4 g = sg[i];
+                for (int i0 = 0; i0 < n; i0 += 128) {
+                    // four independent g per lane: loads and tests overlap, ballots are consumed in table order
+                    unsigned masks[4];
+                    bool cands[4];
+                    float4 gk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        gk[k] = lds_f4(tile_s + 16u * (uint32_t)min(i0 + 32 * k + lane, n - 1));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + 32 * k + lane;
+                        const float4 g = gk[k];
                         const float z = fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z));
-                        const float r2 = fmaxf(fmaf(-z, z, g.w), 0.0f);
-                        if (p.prec == 0.0) {
-                            // z_sphere = r_s - sqrt(r_s^2 - r^2) in the cancellation-free form
-                            const float zs = __fdividef(r2, rs + sqrtf(fmaf(rs, rs, -r2)));
-                            cand = fabsf(zs - z) < thr;
+                        const float r2 = fmaf(-z, z, g.w);
+                        const float u = z + thr, v = z - thr;
+                        bool c;
+                        if (!prec_on) {
+                            // |s| < t  <=>  f(z + t) < 0 < f(z - t),  f(u) = r^2 + u (u - 2 r_s)
+                            c = (fmaf(u, u - two_rs, r2) < 0.0f) && (fmaf(v, v - two_rs, r2) > 0.0f);
                         } else {
-                            const float r = sqrtf(r2);
-                            const float qu = r * (r + 2.0f * P_t), qd = r * (r - 2.0f * P_t);
-                            const float up = __fdividef(qu, P_z + sqrtf(fmaf(P_z, P_z, -qu)));
-                            const float dn = __fdividef(qd, P_z + sqrtf(fmaf(P_z, P_z, -qd)));
-                            cand = (z - thr <= up) && (z + thr >= dn);
+                            // z - t <= z_up(r) and z + t >= z_do(r) (simulation_generator.py:365-375), same algebra
+                            // with the tilted sphere centre (P_t, P_z)
+                            const float r = sqrtf(fmaxf(r2, 0.0f)), two_rpt = 2.0f * r * P_t;
+                            c = (r2 + two_rpt + v * (v - 2.0f * P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * P_z) <= 0.0f);
                         }
+                        cands[k] = c && (i < n);
+                        masks[k] = __ballot_sync(0xffffffffu, cands[k]);
                     }
-                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
-                    if (mask) {
-                        if (cand) list[n_list + __popc(mask & ((1u << lane) - 1u))] = t * tile_g + i;
+                    if ((masks[0] | masks[1] | masks[2] | masks[3]) == 0u) continue;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned mask = masks[k];
+                        if (mask == 0u) continue;
+                        if (cands[k])
+                            sts_u32(list_s + 4u * (uint32_t)(n_list + __popc(mask & ((1u << lane) - 1u))),
+                                    (uint32_t)(t * tile_g + i0 + 32 * k + lane));
                         n_list += __popc(mask);
                         __syncwarp();
                         if (n_list >= 32) {
