@@ -72,6 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy; bytes must be a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -252,6 +252,19 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
 # ----------------------------------------------------------------------------------------------
 # K3
 # ----------------------------------------------------------------------------------------------
+_TICKETS = {}
+
+
+def _ticket(dev):
+    """Two zeroed int32 words per (device, stream) that ds_render uses to hand templates to CTAs; every
+    launch leaves them zero, so they are allocated once."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(2, dtype=torch.int32, device=dev)
+    return t
+
+
 def gaussian_radius(sigma, truncate=4.0):
     """scipy.ndimage.gaussian_filter1d: lw = int(truncate * sd + 0.5)."""
     return int(truncate * float(sigma) + 0.5)
@@ -271,7 +284,7 @@ def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_an
         _stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), _cabi.ptr(intensity), H, W,
         float(calibration), float(center[0]), float(center[1]), float(in_plane_angle), int(bool(mirrored)),
         int(bool(fast)), float(sigma), gaussian_radius(sigma), float(clip_threshold), int(bool(normalize)),
-        _cabi.ptr(out))
+        _cabi.ptr(out), _cabi.ptr(_ticket(dev)))
     _cabi.check(rc, "ds_render")
     return out
 

@@ -130,7 +130,9 @@ int ds_render(void *stream,
               double calibration, double cx, double cy, double in_plane_angle_deg, int32_t mirrored,
               int32_t fast, double sigma, int32_t radius,
               double clip_threshold, int32_t normalize,
-              float *images /*[n_tmpl][H][W]*/);
+              float *images /*[n_tmpl][H][W]*/,
+              int32_t *ticket /*[2] device scratch: zero before the first call, left zero by every call; one
+                                 per concurrently used stream (templates are handed to CTAs dynamically)*/);
 
 /*
  * Polar flattening of the packed result for template matching.
