@@ -333,10 +333,15 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
     }
 }
 
+static int pipe_max_cap() {
+    const char *e = getenv("DS_RENDER_PIPE_MAXCAP");
+    return e ? atoi(e) : 64;
+}
+
 // Returns 1 if the pipelined kernel was launched, 0 if the configuration is not eligible, < 0 on error.
 int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     const int n_regions = ((p.W + RN_RW - 1) / RN_RW) * ((p.H + RN_RH - 1) / RN_RH);
-    if (p.cap > 64 || n_regions > 1024 || p.radius >= p.W || p.radius >= p.H) return 0;
+    if (p.cap > pipe_max_cap() || n_regions > 1024 || p.radius >= p.W || p.radius >= p.H) return 0;
     const int slot_bytes = (32 + p.cap * 8 + n_regions + 15) & ~15;
     const size_t smem = (size_t)4 * p.n4 * 16 + (p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 +
                         (size_t)p.cap * 8 + (size_t)RP_SLOTS * slot_bytes;
