@@ -99,8 +99,13 @@ struct WarpState {
 };
 
 // Refine up to 32 candidates (one per lane) in float64 and append the survivors to the output row.
+// MODEL >= 0 fixes the shape factor at compile time (no precession); MODEL < 0 is the general kernel
+// (runtime model, precession cut, closed-form or numerically averaged precession shape factor).
+template <int MODEL>
 __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot, bool have, int gi, int lane,
                                        const double *__restrict__ s_cos) {
+    constexpr bool GENERAL = MODEL < 0;
+    const int model = GENERAL ? p.model : MODEL;
     bool keep = false;
     double x = 0, y = 0, z = 0, s = 0, I = 0, r_spot = 0;
     if (have) {
@@ -113,7 +118,7 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
         r_spot = sqrt(x * x + y * y);
         const double z_sphere = -sqrt(p.rs * p.rs - r_spot * r_spot) + p.rs;
         s = z_sphere - z;
-        if (p.prec == 0.0) {
+        if (!GENERAL || p.prec == 0.0) {
             keep = fabs(s) < p.s_max;  // :364 strict
         } else {                       // :365-375
             const double P_z = p.rs * cos(p.prec), P_t = p.rs * sin(p.prec);
@@ -123,7 +128,7 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
         }
     }
     double sf = 1.0;
-    if (p.n_quad > 0) {
+    if (GENERAL && p.n_quad > 0) {
         // _shape_factor_precession (shape_factor_models.py:222-269): (1 / 2 pi) int_0^2pi f(s + r phi cos t) dt.
         // The integrand is even and periodic in t, so the midpoint rule on [0, pi] (Gauss-Chebyshev in
         // u = cos t) converges geometrically for the smooth models and as 1/n^2 for the kinked ones; the
@@ -134,13 +139,13 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
             const double amp = __shfl_sync(0xffffffffu, r_spot, c) * p.prec;
             double acc = 0.0;
             for (int j = lane; j < p.n_quad; j += 32)
-                acc += shape_factor(p.model, sc + amp * s_cos[j], p.width, p.minima, 0.0, 0.0);
+                acc += shape_factor(model, sc + amp * s_cos[j], p.width, p.minima, 0.0, 0.0);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == c) sf = acc / (double)p.n_quad;
         }
     } else if (keep) {
-        sf = shape_factor(p.model, s, p.width, p.minima, r_spot, p.prec);
+        sf = shape_factor(model, s, p.width, p.minima, r_spot, GENERAL ? p.prec : 0.0);
     }
     if (keep) I = sf * __ldg(p.g_I0 + gi);
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
@@ -158,13 +163,16 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
     w.max_I = fmax(w.max_I, warp_max(keep ? I : -INFINITY));
 }
 
-__global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p, const int n_tiles,
-                                                               const int tile_g) {
+template <int MODEL>
+__global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kernel(const SimParams p, const int n_tiles,
+                                                                  const int tile_g) {
+    constexpr bool GENERAL = MODEL < 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s_tile[2] = {reinterpret_cast<float4 *>(smem_raw),
                          reinterpret_cast<float4 *>(smem_raw) + (n_tiles > 1 ? tile_g : 0)};
     double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1));
-    for (int j = threadIdx.x; j < p.n_quad; j += SIM_THREADS) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
+    if (GENERAL)
+        for (int j = threadIdx.x; j < p.n_quad; j += SIM_THREADS) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_list[SIM_WARPS][64];
 
@@ -192,8 +200,8 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
 
     const float two_rs = 2.0f * (float)p.rs;
     const float thr = (float)p.s_max + p.coarse_margin;
-    const bool prec_on = p.prec != 0.0;
-    const float P_z = (float)(p.rs * cos(p.prec)), P_t = (float)(p.rs * sin(p.prec));
+    const bool prec_on = GENERAL && p.prec != 0.0;
+    const float P_z = GENERAL ? (float)(p.rs * cos(p.prec)) : 0.f, P_t = GENERAL ? (float)(p.rs * sin(p.prec)) : 0.f;
     const uint32_t tile_base_s = smem_u32(smem_raw);
     int local_max_count = 0;
 
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
                         n_list += __popc(mask);
                         __syncwarp();
                         if (n_list >= 32) {
-                            refine(p, w, rot, true, list[lane], lane, s_cos);
+                            refine<MODEL>(p, w, rot, true, list[lane], lane, s_cos);
                             const int rest = n_list - 32;
                             const int carry = (lane < rest) ? list[32 + lane] : 0;
                             __syncwarp();
@@ -289,13 +297,13 @@ __global__ void __launch_bounds__(SIM_THREADS) simulate_kernel(const SimParams p
             if (n_tiles > 1) __syncthreads();  // everyone is done with `buf` before it is refilled
         }
         if (active) {
-            if (n_list > 0) refine(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
+            if (n_list > 0) refine<MODEL>(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
             __syncwarp();
             local_max_count = max(local_max_count, w.n_out);
             // ---- threshold: keep I > max(I) * min_intensity (simulation_generator.py:237), in place
             const int n_stored = min(w.n_out, p.cap);
             int n_keep = 0;
-            if (p.model == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0) {  // threshold disabled
+            if ((GENERAL ? p.model : MODEL) == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0) {  // threshold disabled
                 n_keep = n_stored;
             } else {
                 const double cut = w.max_I * p.min_intensity;
@@ -414,16 +422,34 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         shape_model != DS_SHAPE_NONE_RETURN_S && shape_model != DS_SHAPE_BINARY)
         p.n_quad = (shape_model == DS_SHAPE_LORENTZIAN || shape_model == DS_SHAPE_ATANC) ? 2048 : 8192;
     const size_t smem = (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1) + (size_t)p.n_quad * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(simulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
-        attr_set = true;
-    }
     const int n_batches = (n_rot + SIM_WARPS - 1) / SIM_WARPS;
-    int blocks_per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, simulate_kernel, SIM_THREADS, smem);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    const int grid = n_batches < num_sms() * blocks_per_sm ? n_batches : num_sms() * blocks_per_sm;
-    simulate_kernel<<<grid, SIM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p, n_tiles, tile_g);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // no precession: one lean kernel per shape factor model; anything with precession: the general kernel
+    auto launch = [&](auto kern, int slot) {
+        static bool attr_set[9] = {false};
+        if (!attr_set[slot]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
+            attr_set[slot] = true;
+        }
+        int blocks_per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SIM_THREADS, smem);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        const int grid = n_batches < num_sms() * blocks_per_sm ? n_batches : num_sms() * blocks_per_sm;
+        kern<<<grid, SIM_THREADS, smem, st>>>(p, n_tiles, tile_g);
+    };
+    if (precession_rad != 0.0) {
+        launch(simulate_kernel<-1>, 8);
+    } else {
+        switch (shape_model) {
+            case DS_SHAPE_BINARY: launch(simulate_kernel<DS_SHAPE_BINARY>, 0); break;
+            case DS_SHAPE_LINEAR: launch(simulate_kernel<DS_SHAPE_LINEAR>, 1); break;
+            case DS_SHAPE_SINC: launch(simulate_kernel<DS_SHAPE_SINC>, 2); break;
+            case DS_SHAPE_SIN2C: launch(simulate_kernel<DS_SHAPE_SIN2C>, 3); break;
+            case DS_SHAPE_ATANC: launch(simulate_kernel<DS_SHAPE_ATANC>, 4); break;
+            case DS_SHAPE_LORENTZIAN: launch(simulate_kernel<DS_SHAPE_LORENTZIAN>, 5); break;
+            case DS_SHAPE_NONE_RETURN_S: launch(simulate_kernel<DS_SHAPE_NONE_RETURN_S>, 7); break;
+            default: launch(simulate_kernel<-1>, 8); break;  // lorentzian_precession with zero angle
+        }
+    }
     return check_launch("ds_simulate");
 }
