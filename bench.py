@@ -193,6 +193,31 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm), samples_in_timed_region=len(inside))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (first-touch then places the pinned
+    host buffers of the end-to-end path next to the GPU's PCIe root).  Best effort; returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]   # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -221,6 +246,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local_rank)   # pinned host buffers land on the GPU's own NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -326,7 +352,8 @@ def main():
         assert torch.equal(out_pin[:64], images[:64].cpu()), "e2e images differ from the device-resident images"
         e2e = dict(value=world * B * n_e2e / (float(te.item()) * 1e-3), unit=UNIT,
                    h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
-                   api="TemplateLibraryBuilder.run_host (pinned host quaternions -> pinned host float32 images)")
+                   api="TemplateLibraryBuilder.run_host (pinned host quaternions -> pinned host float32 images)",
+                   numa_node=numa)
 
     if rank != 0:
         if world > 1:
