@@ -217,3 +217,66 @@ def test_render_graphite_golden(eng, golden_dir):
                      center=(64, 64))[0].cpu().numpy()
     old = np.load(golden_dir / "old_simulation.npz")["image"]
     assert np.abs(img - old).max() <= IMG_ATOL
+
+
+# --------------------------------------------------------------------------- K3 schedule variants
+@pytest.mark.parametrize("variant", ["pipe", "G8", "G4", "G2", "G1"])
+@pytest.mark.parametrize("shape,sigma", [((256, 256), 10.0), ((144, 144), 3.0), ((90, 130), 2.0)])
+def test_render_schedule_variants_agree_with_oracle(eng, monkeypatch, variant, shape, sigma):
+    """The warp-specialised pipelined kernel and every group size of the phase-synchronous kernel are the
+    same arithmetic under different schedules (130 is not a multiple of 4: scalar-store instantiation)."""
+    import torch
+    if variant == "pipe":
+        monkeypatch.delenv("DS_RENDER_GROUP", raising=False)
+        monkeypatch.setenv("DS_RENDER_PIPE", "1")
+    else:
+        monkeypatch.setenv("DS_RENDER_GROUP", variant[1:])
+    phase = cases.phase("fe3c")
+    gs = K.GSet(phase.structure, 1.2, True)
+    wl = K.get_electron_wavelength(200)
+    q = random_quats(40, 21)   # more templates than one CTA holds in flight: exercises the ticket hand-out
+    cal = 1.2 / (min(shape) // 2)
+    refs, X, I, cnt = [], np.zeros((len(q), 64, 3)), np.zeros((len(q), 64)), np.zeros(len(q), np.int32)
+    for r in range(len(q)):
+        ref = K.simulate_rotation(phase.structure, gs, oracle_G_from_active_quat(q[r]), wl, 0.01)
+        n = len(ref["intensity"])
+        assert n <= 64
+        X[r, :n], I[r, :n], cnt[r] = ref["xyz"], ref["intensity"], n
+        refs.append(K.diffraction_pattern(ref["xyz"], ref["intensity"], shape, sigma=sigma, calibration=cal))
+    dev = eng.device()
+    for normalize in (True, False):
+        out = eng.render(torch.as_tensor(cnt, device=dev), torch.as_tensor(X, device=dev),
+                         torch.as_tensor(I, device=dev), shape, sigma, cal, (shape[1] // 2, shape[0] // 2),
+                         normalize=normalize).cpu().numpy()
+        for r in range(len(q)):
+            ref = refs[r] if normalize else K.diffraction_pattern(X[r, :cnt[r]], I[r, :cnt[r]], shape, sigma=sigma,
+                                                                  calibration=cal, normalize=False)
+            assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1e-30), (variant, r)
+    # twice on the same stream: the ticket words re-arm themselves
+    again = eng.render(torch.as_tensor(cnt, device=dev), torch.as_tensor(X, device=dev),
+                       torch.as_tensor(I, device=dev), shape, sigma, cal, (shape[1] // 2, shape[0] // 2),
+                       normalize=False).cpu().numpy()
+    np.testing.assert_array_equal(again, out)
+
+
+def test_edge_sizes(eng):
+    """Zero rotations, zero templates, an empty reciprocal set."""
+    import torch
+    phase = cases.phase("si")
+    gs, gt = _gtable_new_api(eng, phase, 1.0, True)
+    wl = K.get_electron_wavelength(200)
+    spots = eng.simulate(gt, np.zeros((0, 4)), wl, 0.01, 0.01, "lorentzian")
+    assert spots.n_rot == 0
+    out = eng.render(spots.count, spots.xyz, spots.intensity, (64, 64), 3.0, 0.01, (32, 32))
+    assert out.shape == (0, 64, 64)
+    r, t, i = eng.polar_flatten(spots.count, spots.xyz, spots.intensity, 0)
+    assert r.shape == (0, 0)
+    # a reciprocal radius so small that only the direct beam is inside the sphere
+    gs0, gt0 = _gtable_new_api(eng, phase, 0.05, True)
+    assert gt0.n == 2
+    s0 = eng.simulate(gt0, random_quats(3, 1), wl, 0.01, 0.01, "lorentzian")
+    assert s0.count.tolist() == [2, 2, 2]
+    gs1, gt1 = _gtable_new_api(eng, phase, 0.05, False)
+    assert gt1.n == 0
+    s1 = eng.simulate(gt1, random_quats(3, 1), wl, 0.01, 0.01, "lorentzian")
+    assert s1.count.tolist() == [0, 0, 0]
