@@ -490,6 +490,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     auto bytes_for = [&](int g) { return (group_fixed + ((n_regions + 3) & ~3) + g * n_regions * 4 + 15) & ~15; };
     while (G < 8 && lut_bytes + (size_t)(RN_WARPS / G) * bytes_for(G) > 96 * 1024) G <<= 1;
     if (wide || (W & 3) != 0) G = 8;
+    if (!fast && G != 1) G = 8;  // the sub-pixel path is instantiated for G = 1 and G = 8 only
     group_bytes = bytes_for(G);
 #define DS_RN(F, GG, WD, V) launch_render<F, GG, WD, V>(p, group_bytes, lut_bytes, st)
     // rows that are not 16-byte aligned (W % 4 != 0) and kernels wider than the image take the

@@ -280,3 +280,22 @@ def test_edge_sizes(eng):
     assert gt1.n == 0
     s1 = eng.simulate(gt1, random_quats(3, 1), wl, 0.01, 0.01, "lorentzian")
     assert s1.count.tolist() == [0, 0, 0]
+
+
+def test_render_slow_path_with_many_spots(eng):
+    """fast=False with a capacity above 32 (group size heuristics pick G = 2/4 for the fast path only; the
+    sub-pixel path exists for G = 1 and 8) -- found by compute-sanitizer memcheck."""
+    import torch
+    rng = np.random.default_rng(7)
+    n, cap, shape = 6, 96, (128, 128)
+    X = np.zeros((n, cap, 3))
+    X[..., :2] = rng.uniform(-0.9, 0.9, (n, cap, 2))
+    I = rng.uniform(50, 500, (n, cap))
+    cnt = np.array([96, 70, 33, 1, 0, 96], np.int32)
+    dev = eng.device()
+    out = eng.render(torch.as_tensor(cnt, device=dev), torch.as_tensor(X, device=dev), torch.as_tensor(I, device=dev),
+                     shape, 2.5, 1 / 64, (63.5, 63.5), fast=False, normalize=False, clip_threshold=1.0).cpu().numpy()
+    for r in range(n):
+        ref = K.diffraction_pattern(X[r, :cnt[r]], I[r, :cnt[r]], shape, sigma=2.5, calibration=1 / 64, fast=False,
+                                    normalize=False, clip_threshold=1.0) if cnt[r] else np.zeros(shape)
+        assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
