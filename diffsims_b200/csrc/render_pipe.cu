@@ -5,10 +5,10 @@
 // max pass -> store pass), so for a sparse template the store stream of an SM pauses during every
 // non-store phase (measured: 0.90 of the HBM peak normalised vs 0.976 without the max pass).  Here the
 // CTA is warp-specialised:
-//   warp 0 ("front")    prepares template k+1: prefetched spot rows (cp.async.bulk) -> projection, last-write-wins
+//   front warp(s)       prepare template k+1: prefetched spot rows (cp.async.bulk) -> projection, last-write-wins
 //                       hash, compaction -> region upper bounds -> max pass over the few regions that can hold
 //                       the maximum -> scale; publishes a slot and arrives on its `full` mbarrier;
-//   warps 1..7 ("render") drain slot k: regions are handed out by a shared-memory ticket, each region is
+//   render warps        drain slot k: regions are handed out by a shared-memory ticket, each region is
 //                       accumulated in registers and streamed out with st.global.cs.v4; every warp arrives on
 //                       the slot's `empty` mbarrier when the ticket runs out.
 // Two slots per CTA, so stores of template k overlap the whole preparation of template k+1.
@@ -16,18 +16,21 @@
 
 namespace ds {
 
-constexpr int RP_SLOTS = 2;
-constexpr int RP_RENDER_WARPS = RN_WARPS - 1;
+// NF front warps (1 for the sparsest patterns, 2 when the preparation of a template is heavier) feed
+// RN_WARPS - NF render warps through 2 NF slots; front f owns the sequence numbers k = f (mod NF).
 
 struct PipeHeader {  // 32 bytes at the start of a slot
     int n_live, n_pass, t, pad0;
     float scale, vmax, pad1, pad2;
 };
 
-template <bool VEC>
-__global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const RenderParams p, const int slot_bytes) {
+template <bool VEC, int NF>
+__global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const RenderParams p, const int slot_bytes,
+                                                                    const int front_bytes) {
+    constexpr int RP_SLOTS = 2 * NF;
+    constexpr int RP_RENDER_WARPS = RN_WARPS - NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[RP_SLOTS], s_empty[RP_SLOTS], s_stage[2];
+    __shared__ __align__(8) uint64_t s_full[RP_SLOTS], s_empty[RP_SLOTS], s_stage_all[NF][2];
     __shared__ int s_ticket[RP_SLOTS];
     __shared__ double s_norm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -36,7 +39,9 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
 
     // ---- shared memory: LUT | front workspace (stage x2, hash, key, inten) | slots ------------------------
     float4 *lut = reinterpret_cast<float4 *>(smem_raw);
-    unsigned char *base = smem_raw + (size_t)4 * p.n4 * sizeof(float4);
+    const int front = warp < NF ? warp : 0;
+    unsigned char *base = smem_raw + (size_t)4 * p.n4 * sizeof(float4) + (size_t)front * front_bytes;
+    uint64_t *s_stage = s_stage_all[front];
     double *stage[2] = {nullptr, nullptr};
     if (p.stage) {
         stage[0] = reinterpret_cast<double *>(base);
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
     int *key = reinterpret_cast<int *>(base);
     base += (size_t)p.cap * 4;
     float *inten = reinterpret_cast<float *>(base);
-    base += (size_t)p.cap * 4;
+    base = smem_raw + (size_t)4 * p.n4 * sizeof(float4) + (size_t)NF * front_bytes;
     unsigned char *slots = base;
     auto slot_header = [&](int s) { return reinterpret_cast<PipeHeader *>(slots + (size_t)s * slot_bytes); };
     auto slot_spots = [&](int s) { return reinterpret_cast<uint2 *>(slots + (size_t)s * slot_bytes + 32); };
@@ -68,8 +73,10 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 mbar_init(&s_empty[s], RP_RENDER_WARPS);
                 s_ticket[s] = 0;
             }
-            mbar_init(&s_stage[0], 1);
-            mbar_init(&s_stage[1], 1);
+            for (int f = 0; f < NF; ++f) {
+                mbar_init(&s_stage_all[f][0], 1);
+                mbar_init(&s_stage_all[f][1], 1);
+            }
             fence_mbar_init();
         }
     }
@@ -88,7 +95,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
 
     const int lx = lane & 7, ly = lane >> 3;
 
-    if (warp == 0) {
+    if (warp < NF) {
         // =============================== front warp ==========================================================
         auto prefetch = [&](int t, int buf) {
             const uint32_t bx = (uint32_t)p.cap * 24u, bi = (uint32_t)p.cap * 8u;
@@ -108,9 +115,9 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             n_next = p.count[t];
             if (p.stage && lane == 0) prefetch(t, 0);
         }
-        int k = 0;
-        for (;; ++k) {
-            const int slot = k % RP_SLOTS, buf = k & 1;
+        for (int j = 0;; ++j) {
+            const int k = j * NF + front;  // global sequence number of this front's j-th template
+            const int slot = k % RP_SLOTS, buf = j & 1;
             if (t >= p.n_tmpl) {  // out of work: hand the render warps a stop slot
                 mbar_wait(&s_empty[slot], ((uint32_t)(k / RP_SLOTS) & 1u) ^ 1u);
                 if (lane == 0) {
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             const double *sxyz = p.xyz + (size_t)t * p.cap * 3;
             const double *sint = p.intensity + (size_t)t * p.cap;
             if (p.stage) {
-                mbar_wait(&s_stage[buf], (uint32_t)(k >> 1) & 1u);
+                mbar_wait(&s_stage[buf], (uint32_t)(j >> 1) & 1u);
                 sxyz = stage[buf];
                 sint = stage[buf] + p.cap * 3;
             }
@@ -270,12 +277,17 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
         }
     } else {
         // =============================== render warps ========================================================
-        for (int k = 0;; ++k) {
+        unsigned done = 0;  // bit f: front f has run out of work
+        for (int k = 0; done != (1u << NF) - 1u; ++k) {
+            if ((done >> (k % NF)) & 1u) continue;
             const int slot = k % RP_SLOTS;
             mbar_wait(&s_full[slot], (uint32_t)(k / RP_SLOTS) & 1u);
             const PipeHeader *hd = slot_header(slot);
             const int t = hd->t;
-            if (t < 0) break;
+            if (t < 0) {
+                done |= 1u << (k % NF);
+                continue;
+            }
             const int n_live = hd->n_live, n_pass = hd->n_pass;
             const float scale = hd->scale, vmax = hd->vmax;
             const unsigned char *flags = slot_flags(slot);
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
 
 static int pipe_max_cap() {
     const char *e = getenv("DS_RENDER_PIPE_MAXCAP");
-    return e ? atoi(e) : 64;
+    return e ? atoi(e) : 128;
 }
 
 // Returns 1 if the pipelined kernel was launched, 0 if the configuration is not eligible, < 0 on error.
@@ -343,21 +355,27 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     const int n_regions = ((p.W + RN_RW - 1) / RN_RW) * ((p.H + RN_RH - 1) / RN_RH);
     if (p.cap > pipe_max_cap() || n_regions > 1024 || p.radius >= p.W || p.radius >= p.H) return 0;
     const int slot_bytes = (32 + p.cap * 8 + n_regions + 15) & ~15;
-    const size_t smem = (size_t)4 * p.n4 * 16 + (p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 +
-                        (size_t)p.cap * 8 + (size_t)RP_SLOTS * slot_bytes;
-    if (smem > 64 * 1024) return 0;
+    const int front_bytes = (int)((p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 + (size_t)p.cap * 8);
+    // one front warp keeps up with the sparsest patterns; above 32 reflections per template two share the work
+    int nf = p.cap <= 32 ? 1 : 2;
+    if (const char *e = getenv("DS_RENDER_FRONTS")) nf = atoi(e) == 2 ? 2 : 1;
+    const size_t smem = (size_t)4 * p.n4 * 16 + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
+    if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
-    auto kern = vec ? render_pipe_kernel<true> : render_pipe_kernel<false>;
-    static bool attr[2] = {false, false};
-    if (smem > 48 * 1024 && !attr[vec]) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr[vec] = true;
+    void (*kern)(RenderParams, int, int) =
+        nf == 1 ? (vec ? render_pipe_kernel<true, 1> : render_pipe_kernel<false, 1>)
+                : (vec ? render_pipe_kernel<true, 2> : render_pipe_kernel<false, 2>);
+    static bool attr[4] = {false, false, false, false};
+    const int slot_id = (nf - 1) * 2 + (vec ? 1 : 0);
+    if (smem > 48 * 1024 && !attr[slot_id]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr[slot_id] = true;
     }
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RN_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = p.n_tmpl < num_sms() * per_sm ? p.n_tmpl : num_sms() * per_sm;
-    kern<<<grid, RN_THREADS, smem, st>>>(p, slot_bytes);
+    kern<<<grid, RN_THREADS, smem, st>>>(p, slot_bytes, front_bytes);
     const int rc = check_launch("ds_render (pipelined)");
     return rc == 0 ? 1 : rc;
 }
