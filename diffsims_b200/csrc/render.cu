@@ -434,7 +434,6 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.xyz = xyz;
     p.intensity = intensity;
     p.cal = calibration;
-    p.inv_cal_unused = 0.0;
     p.cx = cx;
     p.cy = cy;
     const double ang = in_plane_angle_deg * (3.141592653589793 / 180.0);

@@ -19,7 +19,7 @@ struct RenderParams {
     const int *count;
     const double *xyz;
     const double *intensity;
-    double inv_cal_unused, cal, cx, cy, ca, sa, mirror;  // mirror = +1 / -1
+    double cal, cx, cy, ca, sa, mirror;  // mirror = +1 / -1
     double sigma, clip;
     int radius;  // fast: taps |k| <= radius
     int normalize;
