@@ -12,7 +12,8 @@ _lib = None
 
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_structure_factors", "ds_pack_gtable",
-           "ds_simulate", "ds_render", "ds_polar_flatten", "ds_beam_grid_num_blocks", "ds_beam_grid")
+           "ds_simulate", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
+           "ds_beam_grid_num_blocks", "ds_beam_grid")
 ABI_VERSION = 1
 
 
@@ -42,6 +43,7 @@ def lib():
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
+    L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]
     L.ds_beam_grid.argtypes = [P, I, I, P, I, P, D, P, P, P, P]
     L.ds_beam_grid_num_blocks.argtypes = [I]
     for s in SYMBOLS[2:]:

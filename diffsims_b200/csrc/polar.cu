@@ -66,7 +66,40 @@ __global__ void polar_flatten_kernel(int n_tmpl, int cap, const int *__restrict_
     }
 }
 
+// Library pixel coordinates, diffsims/generators/library_generator.py:129-132 with
+// DiffractionSimulation.calibrated_coordinates (diffsims/sims/diffraction_simulation.py:143-149):
+// rint((xy + offset) / calibration + half_shape) as int32; rint is round-half-to-even like numpy's.
+__global__ void pixel_coords_kernel(int n_tmpl, int cap, const int *__restrict__ count,
+                                    const double *__restrict__ xyz, double cal_x, double cal_y, double off_x,
+                                    double off_y, double half_x, double half_y, int *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_tmpl * cap) return;
+    const int t = (int)(i / cap), j = (int)(i % cap);
+    int px = 0, py = 0;
+    if (j < min(count[t], cap)) {
+        px = (int)rint((xyz[3 * i] + off_x) / cal_x + half_x);
+        py = (int)rint((xyz[3 * i + 1] + off_y) / cal_y + half_y);
+    }
+    out[2 * i] = px;
+    out[2 * i + 1] = py;
+}
+
 }  // namespace ds
+
+extern "C" int ds_library_pixel_coords(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count,
+                                       const double *xyz, double calibration_x, double calibration_y,
+                                       double offset_x, double offset_y, double half_shape_x, double half_shape_y,
+                                       int32_t *pixel_coords) {
+    using namespace ds;
+    DS_REQUIRE(n_tmpl >= 0 && cap > 0, "ds_library_pixel_coords: bad sizes");
+    DS_REQUIRE(calibration_x != 0.0 && calibration_y != 0.0, "ds_library_pixel_coords: calibration cannot be zero");
+    if (n_tmpl == 0) return 0;
+    const long long total = (long long)n_tmpl * cap;
+    pixel_coords_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_tmpl, cap, count, xyz, calibration_x, calibration_y, offset_x, offset_y, half_shape_x, half_shape_y,
+        pixel_coords);
+    return check_launch("ds_library_pixel_coords");
+}
 
 extern "C" int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const double *xyz,
                                 const double *intensity, int32_t max_spots, int32_t n_radial,

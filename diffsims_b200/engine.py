@@ -310,3 +310,17 @@ def polar_flatten(count, xyz, intensity, max_spots, radial_axes=None, azimuthal_
         _cabi.ptr(r), _cabi.ptr(t), _cabi.ptr(i))
     _cabi.check(rc, "ds_polar_flatten")
     return r, t, i
+
+
+def library_pixel_coords(count, xyz, calibration, half_shape, offset=(0.0, 0.0)):
+    """rint((xy + offset) / calibration + half_shape) for every stored reflection: int32 [n, cap, 2]."""
+    dev = xyz.device
+    n, cap = xyz.shape[0], xyz.shape[1]
+    cal = np.broadcast_to(np.asarray(calibration, float), (2,))
+    half = np.broadcast_to(np.asarray(half_shape, float), (2,))
+    out = torch.empty((n, cap, 2), dtype=torch.int32, device=dev)
+    rc = _cabi.lib().ds_library_pixel_coords(_stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), float(cal[0]),
+                                             float(cal[1]), float(offset[0]), float(offset[1]), float(half[0]),
+                                             float(half[1]), _cabi.ptr(out))
+    _cabi.check(rc, "ds_library_pixel_coords")
+    return out

@@ -3,6 +3,7 @@
 Python loop over orientations.  ``VectorLibraryGenerator`` is a different algorithm and out of scope."""
 import numpy as np
 
+from .. import engine
 from ..libraries.diffraction_library import DiffractionLibrary
 from ..sims.diffraction_simulation import DiffractionSimulation
 
@@ -28,6 +29,7 @@ class DiffractionLibraryGenerator:
             gt, spots = diffractor.calculate_ed_data_batch(
                 structure, reciprocal_radius, orientations, max_excitation_error, shape_factor_width,
                 debye_waller_factors)
+            pix = engine.library_pixel_coords(spots.count, spots.xyz, calibration, half_shape).cpu().numpy()
             count = spots.count.cpu().numpy()
             xyz = spots.xyz.cpu().numpy()
             inten = spots.intensity.cpu().numpy()
@@ -43,8 +45,9 @@ class DiffractionLibraryGenerator:
                     with_direct_beam=with_direct_beam)
                 simulation.calibration = calibration
                 simulations[i] = simulation
-                # :129-132
-                pixel_coords[i] = np.rint(simulation.calibrated_coordinates[:, :2] + half_shape).astype(int)
+                # :129-132, computed for the whole library by ds_library_pixel_coords; the direct-beam mask of
+                # the container (with_direct_beam=False hides the (000) row) applies to the pixel list as well
+                pixel_coords[i] = pix[i, :n][simulation.direct_beam_mask].astype(int)
                 intensities[i] = simulation.intensities
 
             diffraction_library[phase_name] = {

@@ -332,26 +332,16 @@ class Simulation2D:
             if radial_axes is not None and azimuthal_axes is not None:
                 r, t = r.astype(int), t.astype(int)
             return r, t, inten
+        # plain DiffractingVector objects (a user-built Simulation2D): same kernel on packed copies; the
+        # iteration is stateful like the reference's (it starts at the current phase / rotation index)
         flattened_vectors = [sim for sim in self]
         max_num_spots = max([v.size for v in flattened_vectors])
-        r_templates = np.zeros((len(flattened_vectors), max_num_spots))
-        theta_templates = np.zeros((len(flattened_vectors), max_num_spots))
-        intensities_templates = np.zeros((len(flattened_vectors), max_num_spots))
-        for i, v in enumerate(flattened_vectors):
-            r, t = v.to_flat_polar()
-            inten = v.intensity
-            if radial_axes is not None and azimuthal_axes is not None:
-                r = get_closest(radial_axes, r)
-                t = get_closest(azimuthal_axes, t)
-                mask = (r < len(radial_axes) - 1) & (t < len(azimuthal_axes) - 1)
-                r, t, inten = r[mask], t[mask], inten[mask]
-            r_templates[i, : len(r)] = r
-            theta_templates[i, : len(r)] = t
-            intensities_templates[i, : len(inten)] = inten
+        count, xyz, inten = pack_vectors(flattened_vectors, engine.device())
+        r, t, i = (o.cpu().numpy() for o in engine.polar_flatten(count, xyz, inten, max_num_spots, radial_axes,
+                                                                 azimuthal_axes))
         if radial_axes is not None and azimuthal_axes is not None:
-            r_templates = np.array(r_templates, dtype=int)
-            theta_templates = np.array(theta_templates, dtype=int)
-        return r_templates, theta_templates, intensities_templates
+            r, t = r.astype(int), t.astype(int)
+        return r, t, i
 
     def _packed_phases(self):
         """The per-phase PackedVectors when the whole result is still packed on the device, else None."""

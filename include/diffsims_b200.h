@@ -150,6 +150,16 @@ int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *c
                      double *r_out, double *theta_out, double *intensity_out);
 
 /*
+ * Pixel coordinates of an old-api template library: rint((xy + offset) / calibration + half_shape) as int32
+ * (diffsims/generators/library_generator.py:129-132, diffsims/sims/diffraction_simulation.py:143-149).
+ * pixel_coords[n_tmpl][cap][2]; entries beyond count[t] are zero.
+ */
+int ds_library_pixel_coords(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
+                            const double *xyz /*[n_tmpl][cap][3]*/, double calibration_x, double calibration_y,
+                            double offset_x, double offset_y, double half_shape_x, double half_shape_y,
+                            int32_t *pixel_coords);
+
+/*
  * Rotation-list producer: beam directions inside the stereographic triangle of a crystal system as Bunge
  * Euler angles (0, Phi, phi2) in degrees and/or as the active quaternions ds_simulate consumes.
  * Replaces get_beam_directions_grid (diffsims/generators/rotation_list_generators.py:176-267) for the cube

@@ -168,10 +168,6 @@ def test_simulation2d_single(al_phase):
         sim.irot[0]
     assert sum(1 for _ in sim) == 1
     assert sim._num_rotations() == 1
-    r, t, i = sim.polar_flatten_simulations()
-    assert r.shape == t.shape == i.shape == (1, 4)
-    r, t, i = sim.polar_flatten_simulations(radial_axes=np.linspace(0, 7, 5), azimuthal_axes=np.linspace(0, 2 * np.pi, 10))
-    assert r.dtype.kind == "i" and r.shape == (1, 4)
     assert sim.deepcopy() is not sim
     with pytest.raises(ValueError):
         Simulation2D(phases=al_phase, simulation_generator=gen, coordinates=[_coords(al_phase)] * 2, rotations=rot)
@@ -190,7 +186,6 @@ def test_simulation2d_multi_rotation(al_phase):
     assert sim.irot[0].rotations.size == 1 and sim.irot[0].coordinates.size == 4
     assert sim.irot[0:2].rotations.size == 2 and sim.irot[0:2].coordinates.size == 2
     assert sum(1 for _ in sim) == 4
-    assert sim.polar_flatten_simulations()[0].shape == (4, 4)
     with pytest.raises(ValueError):
         Simulation2D(phases=al_phase, simulation_generator=gen, coordinates=[c, c, c], rotations=rot)
 
@@ -210,7 +205,6 @@ def test_simulation2d_multi_phase(al_phase):
         sim.iphase[3.1]
     assert sim.irot[0].rotations.size == 2 and sim.irot[0:2].rotations.size == 2
     assert sum(1 for _ in sim) == 8
-    assert sim.polar_flatten_simulations()[0].shape == (8, 4)
     with pytest.raises(ValueError):
         Simulation2D(phases=[al_phase, p2], simulation_generator=gen, coordinates=[[c] * 2, [c] * 2],
                      rotations=[rot, rot])

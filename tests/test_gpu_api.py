@@ -412,6 +412,22 @@ def test_polar_flatten_packed_matches_object_path(axes):
                              simulation_generator=gen)
         assert plain._packed_phases() is None
         slow = plain.polar_flatten_simulations(**kw)
+        if not axes:   # independent numpy evaluation of to_flat_polar (_diffracting_vector.py:186-194)
+            vecs = [v for pv in sim.coordinates for v in pv] if sim.has_multiple_phases else list(sim.coordinates)
+            for row, v in enumerate(vecs):
+                np.testing.assert_allclose(fast[0][row, : v.size], np.hypot(v.data[:, 0], v.data[:, 1]), rtol=1e-14)
+                np.testing.assert_allclose(fast[1][row, : v.size], np.arctan2(v.data[:, 1], v.data[:, 0]), rtol=1e-13,
+                                           atol=1e-15)
+                np.testing.assert_array_equal(fast[2][row, : v.size], v.intensity)
+        else:
+            vecs = [v for pv in sim.coordinates for v in pv] if sim.has_multiple_phases else list(sim.coordinates)
+            from diffsims_b200.simulations import get_closest
+            for row, v in enumerate(vecs):
+                rr_, tt_ = v.to_flat_polar()
+                ri, ti = get_closest(kw["radial_axes"], rr_), get_closest(kw["azimuthal_axes"], tt_)
+                m = (ri < len(kw["radial_axes"]) - 1) & (ti < len(kw["azimuthal_axes"]) - 1)
+                np.testing.assert_array_equal(fast[0][row, : m.sum()], ri[m])
+                np.testing.assert_array_equal(fast[1][row, : m.sum()], ti[m])
         for a, b in zip(fast, slow):
             assert a.shape == b.shape and a.dtype == b.dtype
             np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
@@ -454,3 +470,31 @@ def test_get_beam_directions_grid_matches_reference(golden_dir):
 def engine_simulate(gt, quat, gen):
     from diffsims_b200 import engine
     return engine.simulate(gt, quat, gen.wavelength, 0.01, 0.01, "lorentzian")
+
+
+def test_polar_flatten_user_built_simulations():
+    """diffsims/tests/simulations/test_simulations2d.py:101-127, :346-355, :472-480 (shapes, axis snapping)."""
+    al = Phase(name="al", space_group=225,
+               structure=Structure(atoms=[Atom("al", [0, 0, 0])], lattice=Lattice(0.405, 0.405, 0.405, 90, 90, 90)))
+    gen = ds.SimulationGenerator(accelerating_voltage=200)
+    coords = DiffractingVector(phase=al, xyz=[[1, 0, 0], [2, 0, 0], [3, 3, 0], [-4, 0, 0], [-5, 0, 0], [-6, 0, 0],
+                                              [-7, 0, 0], [-8, 0, 0]], intensity=[1, 2, 3, 4, 5, 6, 7, 8])
+    sim = Simulation2D(phases=al, simulation_generator=gen, coordinates=coords,
+                       rotations=Rotation.from_euler([[0, 45, 0]], degrees=True))
+    r, t, i = sim.polar_flatten_simulations()
+    assert r.shape == t.shape == i.shape == (1, 8)
+    np.testing.assert_allclose(r[0], np.hypot(coords.data[:, 0], coords.data[:, 1]))
+    np.testing.assert_allclose(t[0], np.arctan2(coords.data[:, 1], coords.data[:, 0]))
+    r, t, i = sim.polar_flatten_simulations(radial_axes=np.linspace(0, 7, 5), azimuthal_axes=np.linspace(0, 2 * np.pi, 10))
+    assert r.shape == t.shape == i.shape == (1, 8) and r.dtype.kind == "i"
+    np.testing.assert_array_equal(r[:, 6:], 0)    # the last two are beyond the radial axis
+    np.testing.assert_array_equal(t[:, 6:], 0)
+    np.testing.assert_array_equal(i[:, 6:], 0)
+    rot4 = Rotation.from_euler([[0, a, 0] for a in (0, 15, 30, 45)], degrees=True)
+    c4 = DiffractingVector(phase=al, xyz=[[1, 0, 0], [0, 1, 0], [1, 1, 0], [1, 1, 1]], intensity=[1, 2, 3, 4])
+    multi = Simulation2D(phases=al, simulation_generator=gen, coordinates=[c4] * 4, rotations=rot4)
+    assert multi.polar_flatten_simulations()[0].shape == (4, 4)
+    p2 = al.deepcopy()
+    p2.name = "al2"
+    mp = Simulation2D(phases=[al, p2], simulation_generator=gen, coordinates=[[c4] * 4, [c4] * 4], rotations=[rot4, rot4])
+    assert mp.polar_flatten_simulations()[0].shape == (8, 4)
