@@ -400,13 +400,15 @@ def main():
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64 (structure factors, excitation error, intensities) + f32 (raster)", data="synthetic",
+                dtype="f64+f32", data="synthetic",
                 config=dict(workload=WORKLOAD["workload"], templates_per_gpu_per_step=B, n_g=int(builder.gtable.n),
                             mean_spots_per_template=mean_spots, spot_capacity=int(builder.cap),
                             l2="each step writes %.1f GB of templates per GPU (>> 126 MB L2), so no input or "
                                "output survives in L2 between steps" % (algo_bytes / 1e9),
                             parallelism=f"rotation list sharded over {world} rank(s), no data-path collective",
-                            launch="one CUDA graph replay per step (4 kernels)" if graph is not None else "4 eager launches per step"),
+                            launch="one CUDA graph replay per step (4 kernels)" if graph is not None else "4 eager launches per step",
+                            dtype_note="float64: structure factors, rotation, excitation error, shape factor, intensities, "
+                                       "projection; float32: coarse cull and the rasterised templates"),
                 roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks.summary())
     print(json.dumps(line))
     if world > 1:
