@@ -1,52 +1,62 @@
-"""``DiffractionLibrary`` (diffsims/libraries/diffraction_library.py:29-178): dict of per-phase
-simulations / orientations / pixel coordinates / intensities, with the reference's pickle io."""
+"""``DiffractionLibrary`` -- per-phase template store of the OLD api.
+
+Behavioural mirror of diffsims/libraries/diffraction_library.py:29-178: a ``dict`` keyed by phase name whose
+values hold the object arrays ``simulations`` / ``orientations`` / ``pixel_coords`` / ``intensities``, plus the
+library-level attributes the generator fills in, ``get_library_entry`` and pickle persistence (with the
+reference's explicit ``safety`` opt-in for loading).
+"""
 import pickle
 
 import numpy as np
 
 __all__ = ["DiffractionLibrary", "load_DiffractionLibrary"]
 
+_ANGLE_TOLERANCE = 1e-2  # summed |delta Euler| below which an orientation counts as found (reference :62)
+
 
 def load_DiffractionLibrary(filename, safety=False):
-    if safety:
-        with open(filename, "rb") as handle:
-            return pickle.load(handle)
-    raise RuntimeError("Unpickling is risky, turn safety to True if you trust the author of this content")
+    """Unpickle a library saved with ``pickle_library``; refuses unless ``safety=True``."""
+    if not safety:
+        raise RuntimeError("Unpickling is risky, turn safety to True if you trust the author of this content")
+    with open(filename, "rb") as fh:
+        return pickle.load(fh)
 
 
 def _get_library_entry_from_angles(library, phase, angles):
-    """First entry whose Euler angles are within 1e-2 (summed absolute difference) of ``angles``."""
-    for orientation_index, orientation in enumerate(library[phase]["orientations"]):
-        if np.sum(np.abs(np.subtract(orientation, angles))) < 1e-2:
-            return orientation_index
+    """Index of the first orientation of ``phase`` within the angle tolerance of ``angles`` (ValueError if none)."""
+    target = np.asarray(angles, dtype=float)
+    for index, euler in enumerate(library[phase]["orientations"]):
+        if np.abs(np.asarray(euler, dtype=float) - target).sum() < _ANGLE_TOLERANCE:
+            return index
     raise ValueError("It appears that no library entry lies with 1e-2 of the target angle")
 
 
 class DiffractionLibrary(dict):
+    """Maps phase name -> simulated diffraction data for every orientation of that phase."""
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self.identifiers = None
-        self.structures = None
-        self.diffraction_generator = None
+        self.identifiers = self.structures = self.diffraction_generator = None
         self.reciprocal_radius = 0.0
         self.with_direct_beam = False
 
     def get_library_entry(self, phase=None, angle=None):
-        if phase is not None:
-            phase_entry = self[phase]
-            orientation_index = _get_library_entry_from_angles(self, phase, angle) if angle is not None else 0
-        elif angle is not None:
-            raise ValueError("To select a certain angle you must first specify a phase")
+        """One entry as a dict with keys ``Sim``, ``intensities``, ``pixel_coords``, ``pattern_norm``.
+
+        Without ``phase`` the first phase is used (an ``angle`` then makes no sense -> ValueError); without
+        ``angle`` the first orientation."""
+        if phase is None:
+            if angle is not None:
+                raise ValueError("To select a certain angle you must first specify a phase")
+            entry, index = next(iter(self.values())), 0
         else:
-            phase_entry = next(iter(self.values()))
-            orientation_index = 0
-        return {
-            "Sim": phase_entry["simulations"][orientation_index],
-            "intensities": phase_entry["intensities"][orientation_index],
-            "pixel_coords": phase_entry["pixel_coords"][orientation_index],
-            "pattern_norm": np.linalg.norm(phase_entry["intensities"][orientation_index]),
-        }
+            entry = self[phase]
+            index = 0 if angle is None else _get_library_entry_from_angles(self, phase, angle)
+        intensities = entry["intensities"][index]
+        return {"Sim": entry["simulations"][index], "intensities": intensities,
+                "pixel_coords": entry["pixel_coords"][index], "pattern_norm": np.linalg.norm(intensities)}
 
     def pickle_library(self, filename):
-        with open(filename, "wb") as handle:
-            pickle.dump(self, handle, protocol=pickle.HIGHEST_PROTOCOL)
+        """Save with the highest pickle protocol (load with ``load_DiffractionLibrary(..., safety=True)``)."""
+        with open(filename, "wb") as fh:
+            pickle.dump(self, fh, protocol=pickle.HIGHEST_PROTOCOL)

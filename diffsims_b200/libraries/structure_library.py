@@ -1,35 +1,30 @@
-"""``StructureLibrary`` (diffsims/libraries/structure_library.py:24-127): structures + orientation lists."""
+"""``StructureLibrary`` -- structures with their orientation lists, input of the OLD library api
+(behavioural mirror of diffsims/libraries/structure_library.py:24-127)."""
 
 __all__ = ["StructureLibrary"]
 
 
 class StructureLibrary:
-    """Identifiers, structures and per-structure lists of Euler angles (rzxz, degrees)."""
+    """``struct_lib[identifier] = (structure, orientations)``; orientations are Euler triples (rzxz, degrees)."""
 
     def __init__(self, identifiers, structures, orientations):
-        if len(identifiers) != len(structures):
-            raise ValueError("Number of identifiers ({}) and structures ({}) must be the same.".format(
-                len(identifiers), len(structures)))
-        if len(identifiers) != len(orientations):
-            raise ValueError("Number of identifiers ({}) and orientations ({}) must be the same.".format(
-                len(identifiers), len(orientations)))
-        self.identifiers = identifiers
-        self.structures = structures
-        self.orientations = orientations
-        self.struct_lib = dict()
-        for ident, struct, ori in zip(identifiers, structures, orientations):
-            self.struct_lib[ident] = (struct, ori)
+        for what, seq in (("structures", structures), ("orientations", orientations)):
+            if len(seq) != len(identifiers):
+                raise ValueError(f"Number of identifiers ({len(identifiers)}) and {what} ({len(seq)}) "
+                                 "must be the same.")
+        self.identifiers, self.structures, self.orientations = identifiers, structures, orientations
+        self.struct_lib = {name: (structure, rotations)
+                           for name, structure, rotations in zip(identifiers, structures, orientations)}
 
     @classmethod
     def from_orientation_lists(cls, identifiers, structures, orientations):
         return cls(identifiers, structures, orientations)
 
     def get_library_size(self, to_print=False):
-        size_library = 0
-        for ident, ori in zip(self.identifiers, self.orientations):
-            size_library += 1 if len(ori) == 1 else len(ori)
-            if to_print:
-                print(ident, "has", len(ori), "number of entries.")
+        """Total number of (structure, orientation) entries; optionally print the per-phase counts."""
+        sizes = [len(rotations) for rotations in self.orientations]
         if to_print:
-            print("\nIn total:", size_library, "number of entries")
-        return size_library
+            for name, n in zip(self.identifiers, sizes):
+                print(name, "has", n, "number of entries.")
+            print("\nIn total:", sum(sizes), "number of entries")
+        return sum(sizes)

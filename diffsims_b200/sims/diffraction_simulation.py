@@ -67,34 +67,27 @@ class DiffractionSimulation:
 
     @property
     def direct_beam_mask(self):
-        """True everywhere if ``with_direct_beam`` else False at the (0, 0, 0) row (:171-179)."""
+        """Rows exposed by ``coordinates`` / ``indices`` / ``intensities``: everything when
+        ``with_direct_beam``, else every row except the all-zero (000) one (reference :171-179)."""
         if self.with_direct_beam:
-            return np.ones_like(self._intensities, dtype=bool)
-        return np.any(self._coordinates, axis=1)
+            return np.ones(self._intensities.shape, dtype=bool)
+        return self._coordinates.any(axis=1)
 
-    @property
-    def indices(self):
-        return self._indices[self.direct_beam_mask]
+    def _masked_view(name):  # noqa: N805  (class-body helper: masked read / masked write of one raw array)
+        raw = "_" + name
 
-    @indices.setter
-    def indices(self, indices):
-        self._indices[self.direct_beam_mask] = indices
+        def getter(self):
+            return getattr(self, raw)[self.direct_beam_mask]
 
-    @property
-    def coordinates(self):
-        return self._coordinates[self.direct_beam_mask]
+        def setter(self, value):
+            getattr(self, raw)[self.direct_beam_mask] = value
 
-    @coordinates.setter
-    def coordinates(self, coordinates):
-        self._coordinates[self.direct_beam_mask] = coordinates
+        return property(getter, setter, doc=f"The {name} of all unmasked points.")
 
-    @property
-    def intensities(self):
-        return self._intensities[self.direct_beam_mask]
-
-    @intensities.setter
-    def intensities(self, intensities):
-        self._intensities[self.direct_beam_mask] = intensities
+    indices = _masked_view("indices")
+    coordinates = _masked_view("coordinates")
+    intensities = _masked_view("intensities")
+    del _masked_view
 
     @property
     def calibrated_coordinates(self):
@@ -108,18 +101,16 @@ class DiffractionSimulation:
         return self._calibration
 
     @calibration.setter
-    def calibration(self, calibration):
-        if calibration is None:
-            pass
-        elif np.all(np.equal(calibration, 0)):
-            raise ValueError("`calibration` cannot be zero.")
-        elif isinstance(calibration, float) or isinstance(calibration, int):
-            calibration = np.array((calibration, calibration))
-        elif len(calibration) == 2:
-            calibration = np.array(calibration)
-        else:
-            raise ValueError("`calibration` must be a float or length-2" "tuple of floats.")
-        self._calibration = calibration
+    def calibration(self, value):
+        if value is not None:
+            if np.all(np.equal(value, 0)):
+                raise ValueError("`calibration` cannot be zero.")
+            if isinstance(value, (float, int)):
+                value = (value, value)
+            elif len(value) != 2:
+                raise ValueError("`calibration` must be a float or length-2tuple of floats.")
+            value = np.array(value)
+        self._calibration = value
 
     def _get_transformed_coordinates(self, angle, center=(0, 0), mirrored=False, units="real"):
         """Translate, rotate or mirror the spot coordinates (:199-215)."""
