@@ -9,13 +9,15 @@ CUT_EPS = 1e-6       # reflections this close to the excitation-error cut may di
 IMG_ATOL = 1e-4      # rendered templates, fraction of peak
 
 
-def compare_spots(ref, got, s_max, rr, prec=False, noise_floor=1e-10):
+def compare_spots(ref, got, s_max, rr, prec=False, noise_floor=1e-10, abs_floor=0.0):
     """ref: oracle dict(g_index, xyz, intensity, excitation_error); got: same keys from the device.
 
     Reflection sets must be identical except for reflections within CUT_EPS of the cut and for
     round-off "reflections" (I < noise_floor * max I, SURVEY.md section 7 hard part 3)."""
     rI, gI = np.asarray(ref["intensity"]), np.asarray(got["intensity"])
-    big = max(rI.max() if rI.size else 0.0, gI.max() if gI.size else 0.0)
+    # ``abs_floor``: when every candidate is a forbidden reflection the pattern consists of |F|^2 ~ 1e-30
+    # round-off only (noise against noise, SURVEY.md section 7 hard part 3); such patterns compare as empty
+    big = max(rI.max() if rI.size else 0.0, gI.max() if gI.size else 0.0, abs_floor / max(noise_floor, 1e-300))
     rk = {int(k): i for i, k in enumerate(ref["g_index"])}
     gk = {int(k): i for i, k in enumerate(got["g_index"])}
     for k in set(rk) ^ set(gk):
