@@ -40,7 +40,7 @@ def lib():
     P, I, D = c_void_p, c_int32, c_double
     L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P]
     L.ds_pack_gtable.argtypes = [P, I, P, P]
-    L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P]
+    L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
     L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]

@@ -18,6 +18,8 @@
 // refine: the Lorentzian's sensitivity dI/I ~ 180 ds near s_max needs ds < 5e-8.
 // Survivors are appended to the padded output row in g-table order; a second in-place ballot compaction
 // applies the max-relative intensity threshold.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ds {
@@ -38,6 +40,12 @@ struct SimParams {
     float coarse_margin;
     int model;
     int n_quad;  // > 0: average `model` over the precession circle with n_quad midpoint nodes on [0, pi]
+    // scan-line mode (n_lines > 0): the table is a set of lattice lines g0 + i * step, i = 0 .. count-1
+    int n_lines;
+    const float4 *line_g0;   // [n_lines] (g0.x, g0.y, g0.z, unused)
+    const int *line_start;   // [n_lines + 1] first table index of each line
+    float step[3];
+    float z_lo, z_hi;        // slab of z' that can hold a reflection (cut + margin included)
     int *count;
     int *g_index;
     double *xyz;
@@ -89,6 +97,19 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// float32 coarse test of one g (z' = R[2,:].g, r^2 = |g|^2 - z'^2): cancellation-free and sqrt-free,
+//   |s| < t  <=>  f(z'+t) < 0 < f(z'-t),  f(u) = r^2 + u (u - 2 r_s);
+// with precession the two-surface test of simulation_generator.py:365-375 in the same algebra around the
+// tilted sphere centre (P_t, P_z).
+__device__ __forceinline__ bool coarse_test(float z, float g2, float thr, float two_rs, bool prec_on, float P_z,
+                                            float P_t) {
+    const float r2 = fmaf(-z, z, g2);
+    const float u = z + thr, v = z - thr;
+    if (!prec_on) return (fmaf(u, u - two_rs, r2) < 0.0f) && (fmaf(v, v - two_rs, r2) > 0.0f);
+    const float r = sqrtf(fmaxf(r2, 0.0f)), two_rpt = 2.0f * r * P_t;
+    return (r2 + two_rpt + v * (v - 2.0f * P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * P_z) <= 0.0f);
 }
 
 struct WarpState {
@@ -163,13 +184,14 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
     w.max_I = fmax(w.max_I, warp_max(keep ? I : -INFINITY));
 }
 
-template <int MODEL>
+template <int MODEL, bool LINES>
 __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kernel(const SimParams p, const int n_tiles,
                                                                   const int tile_g) {
     constexpr bool GENERAL = MODEL < 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s_tile[2] = {reinterpret_cast<float4 *>(smem_raw),
                          reinterpret_cast<float4 *>(smem_raw) + (n_tiles > 1 ? tile_g : 0)};
+    // (in scan-line mode the host passes tile_g = bytes of the line tables / 16, n_tiles = 1)
     double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1));
     if (GENERAL)
         for (int j = threadIdx.x; j < p.n_quad; j += SIM_THREADS) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
@@ -193,7 +215,19 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
         }
     };
 
-    if (n_tiles == 1) {  // resident table: one bulk copy for the CTA's lifetime
+    const int *s_lstart = nullptr;
+    if (LINES) {
+        // line table (g0 as float4) + line starts, resident for the CTA's lifetime
+        const uint32_t b0 = (uint32_t)p.n_lines * 16u, b1 = (uint32_t)((p.n_lines + 1 + 3) & ~3) * 4u;
+        int *dst1 = reinterpret_cast<int *>(smem_raw + b0);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar[0], b0 + b1);
+            bulk_g2s(smem_raw, p.line_g0, b0, &s_bar[0]);
+            bulk_g2s(dst1, p.line_start, b1, &s_bar[0]);
+        }
+        mbar_wait(&s_bar[0], 0);
+        s_lstart = dst1;
+    } else if (n_tiles == 1) {  // resident table: one bulk copy for the CTA's lifetime
         issue(0, 0);
         mbar_wait(&s_bar[0], 0);
     }
@@ -233,6 +267,128 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
         int *list = s_list[warp];
         const uint32_t list_s = smem_u32(list);
 
+        // append `cand` lanes' table indices to the warp's candidate list in lane order; refine full warps
+        auto append = [&](bool cand, int index) {
+            const unsigned mask = __ballot_sync(0xffffffffu, cand);
+            if (mask == 0u) return;
+            if (cand) sts_u32(list_s + 4u * (uint32_t)(n_list + __popc(mask & ((1u << lane) - 1u))), (uint32_t)index);
+            n_list += __popc(mask);
+            __syncwarp();
+            if (n_list >= 32) {
+                refine<MODEL>(p, w, rot, true, list[lane], lane, s_cos);
+                const int rest = n_list - 32;
+                const int carry = (lane < rest) ? list[32 + lane] : 0;
+                __syncwarp();
+                list[lane] = carry;
+                n_list = rest;
+                __syncwarp();
+            }
+        };
+
+        if (LINES) {
+            // ---- scan-line cull: a lattice line g0 + i step crosses the slab z_lo <= z' <= z_hi in one short
+            // index interval, found in closed form; only those entries see the exact float32 test.  One lane per
+            // line, 32 lines per step, candidates emitted in table order (lane order, ascending i).
+            if (active) {
+                const float bz = fmaf(mz0, p.step[0], fmaf(mz1, p.step[1], mz2 * p.step[2]));  // dz' per index
+                const bool parallel = fabsf(bz) < 1e-3f;
+                const float inv_b = parallel ? 0.0f : 1.0f / bz;
+                for (int L0 = 0; L0 < p.n_lines; L0 += 32) {
+                    const int L = L0 + lane;
+                    int start = 0, cnt = 0, ilo = 0;
+                    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (L < p.n_lines) {
+                        g0 = lds_f4(tile_base_s + 16u * (uint32_t)L);
+                        start = s_lstart[L];
+                        const int len = s_lstart[L + 1] - start;
+                        const float a = fmaf(mz0, g0.x, fmaf(mz1, g0.y, mz2 * g0.z));
+                        int ihi;
+                        if (!parallel) {
+                            float t0 = (p.z_lo - a) * inv_b, t1 = (p.z_hi - a) * inv_b;
+                            if (t0 > t1) {
+                                const float tmp = t0;
+                                t0 = t1;
+                                t1 = tmp;
+                            }
+                            ilo = max(0, (int)ceilf(t0 - 4e-3f));
+                            ihi = min(len - 1, (int)floorf(t1 + 4e-3f));
+                        } else {  // the line runs (almost) parallel to the slab: all of it or nothing
+                            const float slack = (float)len * fabsf(bz);
+                            const bool inside = a >= p.z_lo - slack && a <= p.z_hi + slack;
+                            ilo = 0;
+                            ihi = inside ? len - 1 : -1;
+                        }
+                        cnt = max(0, ihi - ilo + 1);
+                    }
+                    const int cmax = warp_max(cnt);
+                    if (cmax == 0) continue;
+                    if (cmax <= 4) {
+                        // common case: every lane tests its (at most four) entries itself, survivors are written
+                        // at prefix-sum offsets so that the list stays in table order
+                        unsigned bits = 0;
+                        for (int r = 0; r < cnt; ++r) {
+                            const float fi = (float)(ilo + r);
+                            const float gx = fmaf(fi, p.step[0], g0.x), gy = fmaf(fi, p.step[1], g0.y),
+                                        gz = fmaf(fi, p.step[2], g0.z);
+                            const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
+                            if (coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t))
+                                bits |= 1u << r;
+                        }
+                        const int mine = __popc(bits);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += up;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (total == 0) continue;
+                        if (n_list + total <= 64) {
+                            int at = n_list + incl - mine;
+                            while (bits) {
+                                const int r = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                sts_u32(list_s + 4u * (uint32_t)at++, (uint32_t)(start + ilo + r));
+                            }
+                            n_list += total;
+                            __syncwarp();
+                            while (n_list >= 32) {
+                                refine<MODEL>(p, w, rot, true, list[lane], lane, s_cos);
+                                const int rest = n_list - 32;
+                                const int carry = (lane < rest) ? list[32 + lane] : 0;
+                                __syncwarp();
+                                list[lane] = carry;
+                                n_list = rest;
+                                __syncwarp();
+                            }
+                            continue;
+                        }
+                        // (more than the list can take at once: fall through to the line-by-line path)
+                    }
+                    // long intervals (zone-axis-like orientations) or a burst: the warp scans one line at a time
+                    for (int src = 0; src < 32; ++src) {
+                        const int c = __shfl_sync(0xffffffffu, cnt, src);
+                        if (c == 0) continue;
+                        const int first = __shfl_sync(0xffffffffu, start + ilo, src);
+                        const int i_first = __shfl_sync(0xffffffffu, ilo, src);
+                        const float hx = __shfl_sync(0xffffffffu, g0.x, src), hy = __shfl_sync(0xffffffffu, g0.y, src),
+                                    hz = __shfl_sync(0xffffffffu, g0.z, src);
+                        for (int m = 0; m < c; m += 32) {
+                            const int r = m + lane;
+                            bool cand = false;
+                            if (r < c) {
+                                const float fi = (float)(i_first + r);
+                                const float gx = fmaf(fi, p.step[0], hx), gy = fmaf(fi, p.step[1], hy),
+                                            gz = fmaf(fi, p.step[2], hz);
+                                const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
+                                cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t);
+                            }
+                            append(cand, first + r);
+                        }
+                    }
+                }
+            }
+        } else {
         if (n_tiles > 1) issue(0, 0);
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = (n_tiles > 1) ? (t & 1) : 0;
@@ -246,55 +402,26 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
             if (active) {
                 for (int i0 = 0; i0 < n; i0 += 128) {
                     // four independent g per lane: loads and tests overlap, ballots are consumed in table order
-                    unsigned masks[4];
                     bool cands[4];
                     float4 gk[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         gk[k] = lds_f4(tile_s + 16u * (uint32_t)min(i0 + 32 * k + lane, n - 1));
+                    bool any = false;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int i = i0 + 32 * k + lane;
                         const float4 g = gk[k];
                         const float z = fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z));
-                        const float r2 = fmaf(-z, z, g.w);
-                        const float u = z + thr, v = z - thr;
-                        bool c;
-                        if (!prec_on) {
-                            // |s| < t  <=>  f(z + t) < 0 < f(z - t),  f(u) = r^2 + u (u - 2 r_s)
-                            c = (fmaf(u, u - two_rs, r2) < 0.0f) && (fmaf(v, v - two_rs, r2) > 0.0f);
-                        } else {
-                            // z - t <= z_up(r) and z + t >= z_do(r) (simulation_generator.py:365-375), same algebra
-                            // with the tilted sphere centre (P_t, P_z)
-                            const float r = sqrtf(fmaxf(r2, 0.0f)), two_rpt = 2.0f * r * P_t;
-                            c = (r2 + two_rpt + v * (v - 2.0f * P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * P_z) <= 0.0f);
-                        }
-                        cands[k] = c && (i < n);
-                        masks[k] = __ballot_sync(0xffffffffu, cands[k]);
+                        cands[k] = coarse_test(z, g.w, thr, two_rs, prec_on, P_z, P_t) && (i0 + 32 * k + lane < n);
+                        any |= cands[k];
                     }
-                    if ((masks[0] | masks[1] | masks[2] | masks[3]) == 0u) continue;
+                    if (!__any_sync(0xffffffffu, any)) continue;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned mask = masks[k];
-                        if (mask == 0u) continue;
-                        if (cands[k])
-                            sts_u32(list_s + 4u * (uint32_t)(n_list + __popc(mask & ((1u << lane) - 1u))),
-                                    (uint32_t)(t * tile_g + i0 + 32 * k + lane));
-                        n_list += __popc(mask);
-                        __syncwarp();
-                        if (n_list >= 32) {
-                            refine<MODEL>(p, w, rot, true, list[lane], lane, s_cos);
-                            const int rest = n_list - 32;
-                            const int carry = (lane < rest) ? list[32 + lane] : 0;
-                            __syncwarp();
-                            list[lane] = carry;
-                            n_list = rest;
-                            __syncwarp();
-                        }
-                    }
+                    for (int k = 0; k < 4; ++k) append(cands[k], t * tile_g + i0 + 32 * k + lane);
                 }
             }
             if (n_tiles > 1) __syncthreads();  // everyone is done with `buf` before it is refilled
+        }
         }
         if (active) {
             if (n_list > 0) refine<MODEL>(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
@@ -380,7 +507,8 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
                            const float *g_f32, const double *g_I0, double g_max, double inv_wavelength, double s_max,
                            double width, int32_t shape_model, double minima_number, double precession_rad,
                            double min_intensity, int32_t cap, int32_t *count, int32_t *g_index, double *xyz,
-                           double *intensity, double *excitation_error, int32_t *max_count) {
+                           double *intensity, double *excitation_error, int32_t *max_count, int32_t n_lines,
+                           const float *line_g0, const int32_t *line_start, const double *line_step_host) {
     using namespace ds;
     DS_REQUIRE(n_rot >= 0 && n_g >= 0 && cap > 0, "ds_simulate: bad sizes (n_rot=%d n_g=%d cap=%d)", n_rot, n_g,
                cap);
@@ -414,8 +542,49 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // <~ 3e-7 |g|; 8e-6 max(1, |g|max) leaves > 20x head-room and admits < 0.1 % extra candidates.
     p.coarse_margin = 8e-6f * (float)(g_max > 1.0 ? g_max : 1.0);
 
-    const int n_tiles = (n_g <= SIM_RESIDENT_MAX_G) ? 1 : (n_g + SIM_TILE_G - 1) / SIM_TILE_G;
-    const int tile_g = (n_tiles == 1) ? (n_g > 0 ? n_g : 1) : SIM_TILE_G;
+    // scan-line mode: the caller described the table as lattice lines (see include/diffsims_b200.h)
+    size_t line_bytes = (size_t)n_lines * 16 + (size_t)((n_lines + 1 + 3) & ~3) * 4;
+    bool lines = n_lines > 0 && line_g0 && line_start && line_step_host && line_bytes <= 96 * 1024 &&
+                 (reinterpret_cast<uintptr_t>(line_g0) & 15) == 0 && (reinterpret_cast<uintptr_t>(line_start) & 15) == 0;
+    // Measured on B200 (tools/bench_configs.py): solving per line only pays when the table is large and a line
+    // crosses the slab in less than about half an index on average; DS_SIM_LINES=0/1 overrides (tests).
+    if (lines) {
+        const double rs = inv_wavelength, gm = g_max < rs ? g_max : rs * 0.999999;
+        const double slab = 2.0 * s_max + rs - sqrt(rs * rs - gm * gm) + 2.0 * rs * sin(fabs(precession_rad)) * gm / rs;
+        const double step = sqrt(line_step_host[0] * line_step_host[0] + line_step_host[1] * line_step_host[1] +
+                                 line_step_host[2] * line_step_host[2]);
+        const char *force = getenv("DS_SIM_LINES");
+        if (force)
+            lines = atoi(force) != 0;
+        else
+            lines = n_g >= 2048 && slab < 0.5 * step;
+    }
+    p.n_lines = lines ? n_lines : 0;
+    p.line_g0 = reinterpret_cast<const float4 *>(line_g0);
+    p.line_start = line_start;
+    p.z_lo = p.z_hi = 0.f;
+    p.step[0] = p.step[1] = p.step[2] = 0.f;
+    if (lines) {
+        for (int k = 0; k < 3; ++k) p.step[k] = (float)line_step_host[k];
+        // slab of z' = (R g).z that can hold a reflection: z_sphere(r) - t <= z' <= z_sphere(r) + t for r in
+        // [0, g_max]; with precession the two tilted-sphere surfaces of simulation_generator.py:365-375
+        const double rs = inv_wavelength, t = s_max + p.coarse_margin, gm = g_max < rs ? g_max : rs * 0.999999;
+        double lo, hi;
+        if (precession_rad == 0.0) {
+            lo = -t;
+            hi = rs - sqrt(rs * rs - gm * gm) + t;
+        } else {
+            const double Pz = rs * cos(precession_rad), Pt = rs * sin(precession_rad);
+            const double rr = gm + Pt < rs ? gm + Pt : rs * 0.999999;
+            lo = Pz - rs - t;                          // min over r of z_do(r), at r = P_t
+            hi = Pz - sqrt(rs * rs - rr * rr) + t;     // max over r of z_up(r), at r = g_max
+        }
+        p.z_lo = (float)(lo - p.coarse_margin);
+        p.z_hi = (float)(hi + p.coarse_margin);
+    }
+
+    const int n_tiles = lines ? 1 : ((n_g <= SIM_RESIDENT_MAX_G) ? 1 : (n_g + SIM_TILE_G - 1) / SIM_TILE_G);
+    const int tile_g = lines ? (int)((line_bytes + 15) / 16) : ((n_tiles == 1) ? (n_g > 0 ? n_g : 1) : SIM_TILE_G);
     // precession with a model other than the closed-form Lorentzian: numerical average over the circle
     p.n_quad = 0;
     if (precession_rad != 0.0 && shape_model != DS_SHAPE_LORENTZIAN_PRECESSION &&
@@ -426,7 +595,7 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // no precession: one lean kernel per shape factor model; anything with precession: the general kernel
     auto launch = [&](auto kern, int slot) {
-        static bool attr_set[9] = {false};
+        static bool attr_set[18] = {false};
         if (!attr_set[slot]) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
             attr_set[slot] = true;
@@ -437,19 +606,27 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         const int grid = n_batches < num_sms() * blocks_per_sm ? n_batches : num_sms() * blocks_per_sm;
         kern<<<grid, SIM_THREADS, smem, st>>>(p, n_tiles, tile_g);
     };
+#define DS_SIM(M, SLOT)                                   \
+    do {                                                  \
+        if (lines)                                        \
+            launch(simulate_kernel<M, true>, 9 + SLOT);   \
+        else                                              \
+            launch(simulate_kernel<M, false>, SLOT);      \
+    } while (0)
     if (precession_rad != 0.0) {
-        launch(simulate_kernel<-1>, 8);
+        DS_SIM(-1, 8);
     } else {
         switch (shape_model) {
-            case DS_SHAPE_BINARY: launch(simulate_kernel<DS_SHAPE_BINARY>, 0); break;
-            case DS_SHAPE_LINEAR: launch(simulate_kernel<DS_SHAPE_LINEAR>, 1); break;
-            case DS_SHAPE_SINC: launch(simulate_kernel<DS_SHAPE_SINC>, 2); break;
-            case DS_SHAPE_SIN2C: launch(simulate_kernel<DS_SHAPE_SIN2C>, 3); break;
-            case DS_SHAPE_ATANC: launch(simulate_kernel<DS_SHAPE_ATANC>, 4); break;
-            case DS_SHAPE_LORENTZIAN: launch(simulate_kernel<DS_SHAPE_LORENTZIAN>, 5); break;
-            case DS_SHAPE_NONE_RETURN_S: launch(simulate_kernel<DS_SHAPE_NONE_RETURN_S>, 7); break;
-            default: launch(simulate_kernel<-1>, 8); break;  // lorentzian_precession with zero angle
+            case DS_SHAPE_BINARY: DS_SIM(DS_SHAPE_BINARY, 0); break;
+            case DS_SHAPE_LINEAR: DS_SIM(DS_SHAPE_LINEAR, 1); break;
+            case DS_SHAPE_SINC: DS_SIM(DS_SHAPE_SINC, 2); break;
+            case DS_SHAPE_SIN2C: DS_SIM(DS_SHAPE_SIN2C, 3); break;
+            case DS_SHAPE_ATANC: DS_SIM(DS_SHAPE_ATANC, 4); break;
+            case DS_SHAPE_LORENTZIAN: DS_SIM(DS_SHAPE_LORENTZIAN, 5); break;
+            case DS_SHAPE_NONE_RETURN_S: DS_SIM(DS_SHAPE_NONE_RETURN_S, 7); break;
+            default: DS_SIM(-1, 8); break;  // lorentzian_precession with zero angle
         }
     }
+#undef DS_SIM
     return check_launch("ds_simulate");
 }

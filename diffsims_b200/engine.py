@@ -148,10 +148,40 @@ class GTable:
     f32: torch.Tensor        # [n,4] float32 device (gx, gy, gz, |g|^2)
     I0: torch.Tensor         # [n]   float64 device, |F(g)|^2
     g_max: float
+    # scan-line description of the table (None when it is not made of lattice lines)
+    line_g0: torch.Tensor | None = None     # [n_lines, 4] float32 device
+    line_start: torch.Tensor | None = None  # [n_lines + 1 (padded)] int32 device
+    line_step: np.ndarray | None = None     # [3] float64 host
+    n_lines: int = 0
 
     @property
     def n(self):
         return self.xyz.shape[0]
+
+
+def find_lines(xyz):
+    """Describe a g table as lattice lines g0 + i * step of consecutive rows, if it is one.
+
+    Both enumerations of the reference list Miller indices with l running fastest, so consecutive rows
+    differ by +-c* except where a line ends (or where (000) was removed).  Returns (starts [n_lines + 1],
+    step [3]) or None when fewer than half of the row-to-row differences are the common step."""
+    n = xyz.shape[0]
+    if n < 64:
+        return None
+    d = np.round(np.diff(xyz, axis=0), 9)
+    uniq, inverse, counts = np.unique(d, axis=0, return_inverse=True, return_counts=True)
+    best = int(np.argmax(counts))
+    if counts[best] < 0.5 * (n - 1) or not np.any(uniq[best]):
+        return None
+    same = inverse.reshape(-1) == best
+    starts = np.concatenate([[0], np.nonzero(~same)[0] + 1, [n]]).astype(np.int32)
+    step = (xyz[1:][same] - xyz[:-1][same]).mean(axis=0)
+    # every row must sit on its line to float32 accuracy
+    L = np.repeat(np.arange(len(starts) - 1), np.diff(starts))
+    i = np.arange(n) - starts[L]
+    if np.abs(xyz[starts[L]] + i[:, None] * step - xyz).max() > 1e-7 * max(1.0, float(np.abs(xyz).max())):
+        return None
+    return starts, step
 
 
 class GTablePlan:
@@ -169,6 +199,16 @@ class GTablePlan:
         self.hkl_d = torch.as_tensor(self.hkl.astype(float), device=dev)
         self.gnorm_d = torch.as_tensor(gnorm, device=dev)
         self.xyz_d = torch.as_tensor(self.xyz_host, device=dev)
+        self.lines = None
+        found = find_lines(self.xyz_host)
+        if found is not None:
+            starts, step = found
+            g0 = np.zeros((len(starts) - 1, 4), dtype=np.float32)
+            g0[:, :3] = self.xyz_host[starts[:-1]]
+            pad = (-len(starts)) % 4
+            starts_p = np.concatenate([starts, np.full(pad, starts[-1], np.int32)]).astype(np.int32)
+            self.lines = (torch.as_tensor(g0, device=dev), torch.as_tensor(starts_p, device=dev),
+                          np.ascontiguousarray(step, dtype=np.float64), len(starts) - 1)
 
     def run(self):
         n = self.xyz_d.shape[0]
@@ -179,7 +219,10 @@ class GTablePlan:
             launch_structure_factors(self.atoms, self.hkl_d, self.gnorm_d, None, None, I0)
             _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), n, _cabi.ptr(self.xyz_d), _cabi.ptr(f32)),
                         "ds_pack_gtable")
-        return GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max)
+        gt = GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max)
+        if self.lines is not None:
+            gt.line_g0, gt.line_start, gt.line_step, gt.n_lines = self.lines
+        return gt
 
 
 def make_gtable(structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):
@@ -239,7 +282,8 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
             float(gt.g_max), 1.0 / float(wavelength), float(s_max), float(width), model_id,
             float(minima_number), float(precession_rad), float(min_intensity), cap,
             _cabi.ptr(count), _cabi.ptr(g_index), _cabi.ptr(xyz), _cabi.ptr(inten), _cabi.ptr(exc),
-            _cabi.ptr(max_count))
+            _cabi.ptr(max_count), int(gt.n_lines), _cabi.ptr(gt.line_g0), _cabi.ptr(gt.line_start),
+            None if gt.line_step is None else gt.line_step.ctypes.data_as(_cabi.c_void_p))
         _cabi.check(rc, "ds_simulate")
         if not check_overflow:
             return SpotTable(count, g_index, xyz, inten, exc, cap)

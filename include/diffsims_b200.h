@@ -95,6 +95,14 @@ int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz /*[n_g][3]*/, 
  * at most `cap`; *max_count (device int32, caller zero-initialised) receives the largest
  * number of reflections any rotation needed, so the caller can retry with cap >= *max_count.
  * excitation_error may be NULL.
+ *
+ * Optional scan-line description of the table (n_lines = 0 / NULL pointers = none): rows line_start[L] ..
+ * line_start[L+1]-1 of the table are the lattice line line_g0[L] + i * line_step (i = 0, 1, ...), i.e. consecutive
+ * Miller indices along one axis, as both g-set enumerations of the reference produce them.  With it the coarse cull
+ * may solve for the short index interval in which each line crosses the Ewald slab instead of testing every row
+ * (same candidates, same order, same float64 refine; used for tables of >= 2048 rows when the slab is thinner than
+ * half a step, DS_SIM_LINES=0/1 in the environment forces it off/on).  line_g0: device float[n_lines][4] (16-byte aligned),
+ * line_start: device int32[n_lines+1] padded to a multiple of 4 entries, line_step_host: HOST double[3].
  */
 int ds_simulate(void *stream,
                 int32_t n_rot, const double *quat /*[n_rot][4]*/,
@@ -108,7 +116,8 @@ int ds_simulate(void *stream,
                 int32_t *count /*[n_rot]*/, int32_t *g_index /*[n_rot][cap]*/,
                 double *xyz /*[n_rot][cap][3]*/, double *intensity /*[n_rot][cap]*/,
                 double *excitation_error /*[n_rot][cap] or NULL*/,
-                int32_t *max_count /*[1]*/);
+                int32_t *max_count /*[1]*/,
+                int32_t n_lines, const float *line_g0, const int32_t *line_start, const double *line_step_host);
 
 /*
  * K3 -- rasterise spot lists into templates.

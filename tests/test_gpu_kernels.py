@@ -119,6 +119,44 @@ def test_simulate_streaming_tiles_large_cell(eng):
         compare_spots(ref, row(spots, r), 0.01, 1.2)
 
 
+@pytest.mark.parametrize("name,rr,s_max,model,prec_deg", [
+    ("si", 2.0, 0.01, "lorentzian", 0.0),
+    ("si", 1.0, 0.05, "linear", 0.0),
+    ("triclinic", 1.5, 0.02, "sinc", 0.0),
+    ("graphite", 2.0, 0.1, "lorentzian", 0.0),
+    ("si", 2.0, 0.01, "lorentzian_precession", 0.5),
+    ("large", 1.2, 0.01, "lorentzian", 0.0),
+])
+def test_simulate_scan_line_cull_is_identical(eng, monkeypatch, name, rr, s_max, model, prec_deg):
+    """The scan-line cull (lattice lines solved for their slab crossing) and the brute-force cull feed the same
+    candidates in the same order to the same float64 refine: identical reflection lists, including for lines
+    parallel to the slab (c* in the detector plane) and zone axes."""
+    phase = cases.phase(name)
+    gs, gt = _gtable_new_api(eng, phase, rr, True)
+    assert gt.n_lines > 0
+    wl = K.get_electron_wavelength(200)
+    q = random_quats(64, 21)
+    q[0] = (1, 0, 0, 0)
+    q[1] = (np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0)     # c* perpendicular to the beam: parallel lines
+    q[2] = (np.cos(np.pi / 4), 0, np.sin(np.pi / 4), 0)
+    q[3] = (np.cos(np.pi / 4 + 2e-4), np.sin(np.pi / 4 + 2e-4), 0, 0)   # almost parallel
+    q[4] = (np.cos(np.pi / 4 + 2e-3), np.sin(np.pi / 4 + 2e-3), 0, 0)
+    out = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DS_SIM_LINES", mode)
+        sp = eng.simulate(gt, q, wl, s_max, s_max, model, precession_rad=np.deg2rad(prec_deg), want_exc=True)
+        out.append(sp)
+    a, b = out
+    assert np.array_equal(a.count.cpu().numpy(), b.count.cpu().numpy())
+    assert int(a.count.sum()) > 0
+    for r in range(len(q)):
+        n = int(a.count[r])
+        assert np.array_equal(a.g_index[r, :n].cpu().numpy(), b.g_index[r, :n].cpu().numpy()), r
+        for field in ("xyz", "intensity", "exc"):  # two template instantiations: fma contraction may differ
+            x, y = getattr(a, field)[r, :n].cpu().numpy(), getattr(b, field)[r, :n].cpu().numpy()
+            assert np.allclose(x, y, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(x).max())), (r, field)
+
+
 def test_simulate_cap_overflow_retry(eng):
     phase = cases.phase("si")
     gs, gt = _gtable_new_api(eng, phase, 5.0, True)
