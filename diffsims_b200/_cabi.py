@@ -13,7 +13,7 @@ _lib = None
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_structure_factors", "ds_pack_gtable",
            "ds_simulate", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
-           "ds_beam_grid_num_blocks", "ds_beam_grid")
+           "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points")
 ABI_VERSION = 1
 
 
@@ -46,9 +46,12 @@ def lib():
     L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]
     L.ds_beam_grid.argtypes = [P, I, I, P, I, P, D, P, P, P, P]
     L.ds_beam_grid_num_blocks.argtypes = [I]
+    L.ds_beam_points.argtypes = [P, I, ctypes.c_int64, P, I, P, D, P, P, P, P]
+    L.ds_beam_points_num_blocks.argtypes = [ctypes.c_int64]
     for s in SYMBOLS[2:]:
         getattr(L, s).restype = c_int32
     L.ds_beam_grid_num_blocks.restype = ctypes.c_int64
+    L.ds_beam_points_num_blocks.restype = ctypes.c_int64
     _lib = L
     return L
 

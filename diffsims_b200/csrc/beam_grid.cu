@@ -9,6 +9,8 @@
 // reference does; the kernel forms the 6 n^2 + 2 cube points in the reference's order (bottom, top, east,
 // west, south, north, two corners), normalises, crops with the three plane tests, and compacts in order:
 // pass 0 counts survivors per block, pass 1 writes them at the scanned block offsets.
+// The uv-sphere, icosahedral and random meshes (:42-93, :378-483) are small host-side vertex lists; ds_beam_points
+// runs the same crop / compaction / conversion on vertices already in device memory.
 #include "common.cuh"
 
 namespace ds {
@@ -17,13 +19,27 @@ struct BeamGridParams {
     int n_i;
     long long n_points;
     const double *i_vals;
+    const double *points;  // non-null: [n_points][3] mesh vertices instead of the cube faces
     int mode;  // 0 no crop (triclinic) | 1 x >= eps (monoclinic, as the reference computes it) | 2 triangle
     double nrm[9];
     double eps;
 };
 
+// crop to the stereographic triangle, rotation_list_generators.py:237-263
+__device__ __forceinline__ bool beam_crop(const BeamGridParams &p, double vx, double vy, double vz) {
+    if (p.mode == 0) return true;
+    if (p.mode == 1) return vx >= p.eps;
+    return (p.nrm[0] * vx + p.nrm[1] * vy + p.nrm[2] * vz >= p.eps) &&
+           (p.nrm[3] * vx + p.nrm[4] * vy + p.nrm[5] * vz >= p.eps) &&
+           (p.nrm[6] * vx + p.nrm[7] * vy + p.nrm[8] * vz >= p.eps);
+}
+
 __device__ __forceinline__ bool beam_point(const BeamGridParams &p, long long idx, double &vx, double &vy,
                                            double &vz) {
+    if (p.points) {
+        vx = p.points[3 * idx], vy = p.points[3 * idx + 1], vz = p.points[3 * idx + 2];
+        return beam_crop(p, vx, vy, vz);
+    }
     const long long nn = (long long)p.n_i * p.n_i;
     const int face = (int)(idx / nn);
     double x, y, z = 1.0;
@@ -46,11 +62,7 @@ __device__ __forceinline__ bool beam_point(const BeamGridParams &p, long long id
     }
     const double inv = sqrt(vx * vx + vy * vy + vz * vz);
     vx /= inv, vy /= inv, vz /= inv;
-    if (p.mode == 0) return true;
-    if (p.mode == 1) return vx >= p.eps;
-    return (p.nrm[0] * vx + p.nrm[1] * vy + p.nrm[2] * vz >= p.eps) &&
-           (p.nrm[3] * vx + p.nrm[4] * vy + p.nrm[5] * vz >= p.eps) &&
-           (p.nrm[6] * vx + p.nrm[7] * vy + p.nrm[8] * vz >= p.eps);
+    return beam_crop(p, vx, vy, vz);
 }
 
 constexpr int BG_THREADS = 256;
@@ -115,23 +127,53 @@ extern "C" int64_t ds_beam_grid_num_blocks(int32_t n_i) {
     return (n + ds::BG_THREADS - 1) / ds::BG_THREADS;
 }
 
+static int beam_launch(void *stream, const char *what, ds::BeamGridParams &p, int32_t pass, int32_t mode,
+                       const double *normals_host, double epsilon, int32_t *block_counts,
+                       const int64_t *block_offsets, double *euler_deg, double *quat_active) {
+    using namespace ds;
+    DS_REQUIRE(mode >= 0 && mode <= 2, "%s: unknown crop mode %d", what, mode);
+    DS_REQUIRE(pass == 0 || pass == 1, "%s: pass must be 0 (count) or 1 (fill)", what);
+    DS_REQUIRE(mode != 2 || normals_host != nullptr, "%s: triangle crop needs three plane normals", what);
+    DS_REQUIRE(block_counts != nullptr && (pass == 0 || block_offsets != nullptr), "%s: null block arrays", what);
+    p.mode = mode;
+    for (int k = 0; k < 9; ++k) p.nrm[k] = normals_host ? normals_host[k] : 0.0;
+    p.eps = epsilon;
+    const long long blocks = (p.n_points + BG_THREADS - 1) / BG_THREADS;
+    beam_grid_kernel<<<(unsigned)blocks, BG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, pass, block_counts, reinterpret_cast<const long long *>(block_offsets), euler_deg, quat_active);
+    return check_launch(what);
+}
+
 extern "C" int ds_beam_grid(void *stream, int32_t pass, int32_t n_i, const double *i_vals, int32_t mode,
                             const double *normals_host, double epsilon, int32_t *block_counts,
                             const int64_t *block_offsets, double *euler_deg, double *quat_active) {
     using namespace ds;
     DS_REQUIRE(n_i > 0 && n_i <= 32768, "ds_beam_grid: n_i out of range");
-    DS_REQUIRE(mode >= 0 && mode <= 2, "ds_beam_grid: unknown crop mode %d", mode);
-    DS_REQUIRE(pass == 0 || pass == 1, "ds_beam_grid: pass must be 0 (count) or 1 (fill)");
-    DS_REQUIRE(mode != 2 || normals_host != nullptr, "ds_beam_grid: triangle crop needs three plane normals");
+    DS_REQUIRE(i_vals != nullptr, "ds_beam_grid: null face grid");
     BeamGridParams p;
     p.n_i = n_i;
     p.n_points = 6ll * n_i * n_i + 2;
     p.i_vals = i_vals;
-    p.mode = mode;
-    for (int k = 0; k < 9; ++k) p.nrm[k] = normals_host ? normals_host[k] : 0.0;
-    p.eps = epsilon;
-    const long long blocks = ds_beam_grid_num_blocks(n_i);
-    beam_grid_kernel<<<(unsigned)blocks, BG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, pass, block_counts, reinterpret_cast<const long long *>(block_offsets), euler_deg, quat_active);
-    return check_launch("ds_beam_grid");
+    p.points = nullptr;
+    return beam_launch(stream, "ds_beam_grid", p, pass, mode, normals_host, epsilon, block_counts, block_offsets,
+                       euler_deg, quat_active);
+}
+
+extern "C" int64_t ds_beam_points_num_blocks(int64_t n_points) {
+    return (n_points + ds::BG_THREADS - 1) / ds::BG_THREADS;
+}
+
+extern "C" int ds_beam_points(void *stream, int32_t pass, int64_t n_points, const double *points, int32_t mode,
+                              const double *normals_host, double epsilon, int32_t *block_counts,
+                              const int64_t *block_offsets, double *euler_deg, double *quat_active) {
+    using namespace ds;
+    DS_REQUIRE(n_points > 0 && n_points <= (1ll << 40), "ds_beam_points: n_points out of range");
+    DS_REQUIRE(points != nullptr, "ds_beam_points: null vertex array");
+    BeamGridParams p;
+    p.n_i = 0;
+    p.n_points = n_points;
+    p.i_vals = nullptr;
+    p.points = points;
+    return beam_launch(stream, "ds_beam_points", p, pass, mode, normals_host, epsilon, block_counts, block_offsets,
+                       euler_deg, quat_active);
 }

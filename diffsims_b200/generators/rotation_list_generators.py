@@ -7,9 +7,11 @@ in the ``ds_beam_grid`` kernel.  ``beam_directions_device`` is the same grid lef
 angles and the active quaternions the simulate kernel consumes -- so that a 3e5 - 1e6 entry rotation list
 never exists as a Python list of tuples.
 
-Only the cube meshes (``normalized_cube``, ``spherified_cube_edge`` -- the default --,
-``spherified_cube_corner``) are implemented; the uv-sphere / icosahedral / random meshes and the
-orix-backed fundamental-zone and local grids are not.
+All six meshes of the reference are available.  The cube meshes (``normalized_cube``, ``spherified_cube_edge``
+-- the default --, ``spherified_cube_corner``) are generated inside the kernel from the 1-D face grid; the
+uv-sphere / icosahedral / random vertex lists come from ``sphere_mesh_generators`` and are cropped and converted
+by ``ds_beam_points``.  The orix-backed fundamental-zone and local grids (``get_fundamental_zone_grid``,
+``get_local_grid``: orix ``get_sample_fundamental`` / ``get_sample_local``) are not built.
 """
 import math
 
@@ -75,17 +77,60 @@ def _crop(crystal_system):
     return 2, np.ascontiguousarray(nrm)
 
 
+def _compact(call, n_blocks, dev, want_euler, want_quaternions):
+    """Two-pass ordered compaction shared by ds_beam_grid / ds_beam_points: count, scan, fill."""
+    counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
+    call(0, counts, None, None, None)
+    incl = torch.cumsum(counts, dim=0, dtype=torch.int64)
+    offsets = (incl - counts).contiguous()
+    n = int(incl[-1].item())
+    euler = torch.empty((n, 3), dtype=torch.float64, device=dev) if want_euler else None
+    quat = torch.empty((n, 4), dtype=torch.float64, device=dev) if want_quaternions else None
+    if n:
+        call(1, counts, offsets, euler, quat)
+    return euler, quat
+
+
+def _points_to_grid(points, crystal_system, want_euler=True, want_quaternions=True):
+    """Crop mesh vertices [N, 3] to the triangle of ``crystal_system`` and convert them on the device."""
+    if crystal_system not in crystal_system_dictionary and crystal_system != "triclinic":
+        raise KeyError(crystal_system)
+    dev = engine.device()
+    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=dev)
+    mode, nrm = _crop(crystal_system)
+    nrm_p = None if nrm is None else nrm.ctypes.data_as(_cabi.c_void_p)
+    lib = _cabi.lib()
+
+    def call(pass_, counts, offsets, euler, quat):
+        _cabi.check(lib.ds_beam_points(engine._stream(), pass_, pts.shape[0], _cabi.ptr(pts), mode, nrm_p, -1e-13,
+                                       _cabi.ptr(counts), _cabi.ptr(offsets), _cabi.ptr(euler), _cabi.ptr(quat)),
+                    "ds_beam_points")
+
+    if pts.shape[0] == 0:
+        empty = lambda k: torch.empty((0, k), dtype=torch.float64, device=dev)  # noqa: E731
+        return (empty(3) if want_euler else None), (empty(4) if want_quaternions else None)
+    return _compact(call, int(lib.ds_beam_points_num_blocks(pts.shape[0])), dev, want_euler, want_quaternions)
+
+
 def beam_directions_device(crystal_system, resolution, mesh="spherified_cube_edge", want_euler=True,
                            want_quaternions=True):
     """Beam-direction grid in HBM: returns (euler_deg [N,3] or None, active_quaternions [N,4] or None)."""
+    from . import sphere_mesh_generators as smg
+    if mesh == "uv_sphere":
+        return _points_to_grid(smg.get_uv_sphere_mesh_vertices(resolution), crystal_system, want_euler,
+                               want_quaternions)
+    if mesh == "icosahedral":
+        return _points_to_grid(smg.get_icosahedral_mesh_vertices(resolution), crystal_system, want_euler,
+                               want_quaternions)
+    if mesh == "random":
+        return _points_to_grid(smg.get_random_sphere_vertices(resolution), crystal_system, want_euler,
+                               want_quaternions)
     if mesh == "spherified_cube_corner":
         grid_type = "spherified_corner"
     elif mesh in ("normalized_cube", "spherified_cube_edge"):
         if crystal_system == "hexagonal":  # :216-218
             resolution = resolution / np.sqrt(2)
         grid_type = "normalized" if mesh == "normalized_cube" else "spherified_edge"
-    elif mesh in ("uv_sphere", "icosahedral", "random"):
-        raise NotImplementedError(f"the mesh {mesh} is not implemented on the device; use a cube mesh")
     else:
         raise NotImplementedError(
             f"The mesh {mesh} is not recognized. Please use: uv_sphere, normalized_cube, "
@@ -96,21 +141,15 @@ def beam_directions_device(crystal_system, resolution, mesh="spherified_cube_edg
     i_vals = torch.as_tensor(np.ascontiguousarray(_face_grid(resolution, grid_type)), device=dev)
     n_i = i_vals.numel()
     mode, nrm = _crop(crystal_system)
-    lib = _cabi.lib()
-    n_blocks = int(lib.ds_beam_grid_num_blocks(n_i))
-    counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
     nrm_p = None if nrm is None else nrm.ctypes.data_as(_cabi.c_void_p)
-    eps = -1e-13
-    _cabi.check(lib.ds_beam_grid(engine._stream(), 0, n_i, _cabi.ptr(i_vals), mode, nrm_p, eps, _cabi.ptr(counts),
-                                 None, None, None), "ds_beam_grid")
-    incl = torch.cumsum(counts, dim=0, dtype=torch.int64)
-    offsets = (incl - counts).contiguous()
-    n = int(incl[-1].item())
-    euler = torch.empty((n, 3), dtype=torch.float64, device=dev) if want_euler else None
-    quat = torch.empty((n, 4), dtype=torch.float64, device=dev) if want_quaternions else None
-    _cabi.check(lib.ds_beam_grid(engine._stream(), 1, n_i, _cabi.ptr(i_vals), mode, nrm_p, eps, _cabi.ptr(counts),
-                                 _cabi.ptr(offsets), _cabi.ptr(euler), _cabi.ptr(quat)), "ds_beam_grid")
-    return euler, quat
+    lib = _cabi.lib()
+
+    def call(pass_, counts, offsets, euler, quat):
+        _cabi.check(lib.ds_beam_grid(engine._stream(), pass_, n_i, _cabi.ptr(i_vals), mode, nrm_p, -1e-13,
+                                     _cabi.ptr(counts), _cabi.ptr(offsets), _cabi.ptr(euler), _cabi.ptr(quat)),
+                    "ds_beam_grid")
+
+    return _compact(call, int(lib.ds_beam_grid_num_blocks(n_i)), dev, want_euler, want_quaternions)
 
 
 def get_beam_directions_grid(crystal_system, resolution, mesh="spherified_cube_edge"):

@@ -185,6 +185,18 @@ int ds_beam_grid(void *stream, int32_t pass, int32_t n_i, const double *i_vals, 
                  const double *normals_host /*[3][3] or NULL*/, double epsilon, int32_t *block_counts,
                  const int64_t *block_offsets, double *euler_deg /*[n][3]*/, double *quat_active /*[n][4]*/);
 
+/*
+ * The same crop / ordered compaction / Euler + quaternion conversion for mesh vertices already in device memory
+ * (points[n_points][3], float64): the uv-sphere, icosahedral and random meshes of
+ * diffsims/generators/sphere_mesh_generators.py:42-93, :378-483 selected by get_beam_directions_grid(mesh=...)
+ * (rotation_list_generators.py:205-235).  Passes and block arrays as for ds_beam_grid, over
+ * ds_beam_points_num_blocks(n_points) blocks.
+ */
+int64_t ds_beam_points_num_blocks(int64_t n_points);
+int ds_beam_points(void *stream, int32_t pass, int64_t n_points, const double *points, int32_t mode,
+                   const double *normals_host, double epsilon, int32_t *block_counts,
+                   const int64_t *block_offsets, double *euler_deg, double *quat_active);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,8 @@ Writes small ``.npz`` files next to this script.  Sources of truth:
 * ``sim_utils.npz``          reference ``utils/sim_utils.py`` ``get_kinematical_intensities``,
                              ``get_points_in_sphere`` on stand-in structures.
 * ``beam_grid.npz``          reference ``generators/rotation_list_generators.get_beam_directions_grid``
-                             (cube meshes) for the seven crystal systems.
+                             (cube, uv-sphere and icosahedral meshes) for the crystal systems, and the
+                             mesh vertices of ``generators/sphere_mesh_generators.py``.
 * ``ed_data.npz``            reference OLD api ``DiffractionGenerator.calculate_ed_data`` +
                              ``DiffractionSimulation.get_diffraction_pattern`` (run with the
                              euler2mat placeholder documented in _ref_loader.py).
@@ -125,6 +126,14 @@ for system in cases.BEAM_GRID_SYSTEMS:
 for system in ("cubic", "hexagonal", "monoclinic"):
     for mesh in ("normalized_cube", "spherified_cube_corner", "spherified_cube_edge"):
         out[f"{mesh}_{system}_5deg"] = rlg.get_beam_directions_grid(system, 5, mesh=mesh)
+smg = ns.sphere_mesh_generators
+for system in ("cubic", "hexagonal", "orthorhombic", "triclinic"):
+    for mesh in ("uv_sphere", "icosahedral"):
+        out[f"{mesh}_{system}_5deg"] = rlg.get_beam_directions_grid(system, 5, mesh=mesh)
+out["vertices_uv_sphere_7deg"] = smg.get_uv_sphere_mesh_vertices(7)
+out["vertices_icosahedral_9deg"] = smg.get_icosahedral_mesh_vertices(9)
+out["vertices_icosahedral_3deg"] = smg.get_icosahedral_mesh_vertices(3)
+out["vertices_random_4deg_seed3"] = smg.get_random_sphere_vertices(4, seed=3)
 np.savez_compressed(HERE / "beam_grid.npz", **out)
 
 for f in sorted(HERE.glob("*.npz")):

@@ -300,3 +300,35 @@ def test_old_api_containers(tmp_path):
         ds.StructureLibrary(["a"], [1, 2], [[(0, 0, 0)]])
     sl = ds.StructureLibrary(["a", "b"], [1, 2], [[(0, 0, 0)], [(0, 0, 0), (1, 1, 1)]])
     assert sl.get_library_size() == 3
+
+
+# ---------------------------------------------------------------- sphere meshes (host vertex lists)
+def test_sphere_mesh_vertices_match_reference(golden_dir):
+    """Vertex lists of the uv-sphere / icosahedral / random / cube meshes: bit-identical to the reference's
+    (golden arrays from sphere_mesh_generators.py) and the sizes its own tests pin
+    (diffsims/tests/generators/test_sphere_mesh_generators.py:34-75, :115-121)."""
+    from diffsims_b200.generators import sphere_mesh_generators as smg
+    from oracle import kinematical as K
+    gold = np.load(golden_dir / "beam_grid.npz")
+    np.testing.assert_array_equal(smg.get_uv_sphere_mesh_vertices(7), gold["vertices_uv_sphere_7deg"])
+    np.testing.assert_array_equal(smg.get_icosahedral_mesh_vertices(9), gold["vertices_icosahedral_9deg"])
+    np.testing.assert_array_equal(smg.get_icosahedral_mesh_vertices(3), gold["vertices_icosahedral_3deg"])
+    np.testing.assert_array_equal(smg.get_random_sphere_vertices(4, seed=3), gold["vertices_random_4deg_seed3"])
+    assert smg.get_random_sphere_vertices(1).shape == (10313, 3)
+    assert not np.allclose(smg.get_random_sphere_vertices(3, seed=7), smg.get_random_sphere_vertices(3, seed=8))
+    for make, n in ((lambda: smg.get_uv_sphere_mesh_vertices(10), 614),
+                    (lambda: smg.get_icosahedral_mesh_vertices(10), 642),
+                    (lambda: smg.get_cube_mesh_vertices(10, "normalized"), 866),
+                    (lambda: smg.get_cube_mesh_vertices(10, "spherified_edge"), 602),
+                    (lambda: smg.get_cube_mesh_vertices(10, "spherified_corner"), 866)):
+        grid = make()
+        assert grid.shape == (n, 3)
+        np.testing.assert_almost_equal(np.sum(grid), 0)
+        assert np.unique(grid, axis=0).shape[0] == n
+    for grid_type in ("normalized", "spherified_edge", "spherified_corner"):
+        np.testing.assert_array_equal(smg.get_cube_mesh_vertices(6, grid_type), K.cube_mesh_vertices(6, grid_type))
+    with pytest.raises(Exception):
+        smg.get_cube_mesh_vertices(10, "non_existant")
+    with pytest.raises(ValueError):
+        smg.get_icosahedral_mesh_vertices(90)
+    assert smg._max_neighbour_angle(np.array([[1.0, 0, 0], [0, 1, 0], [0, 1, 1], [1, 0, 1]])) == pytest.approx(45.0)  # :84-112

@@ -467,6 +467,39 @@ def test_get_beam_directions_grid_matches_reference(golden_dir):
     np.testing.assert_allclose([t[1] for t in g], 45.0, atol=1e-2)
 
 
+@pytest.mark.parametrize("mesh", ["uv_sphere", "normalized_cube", "spherified_cube_edge", "spherified_cube_corner",
+                                  "icosahedral", "random"])
+def test_get_beam_directions_grid_all_meshes(mesh):
+    """diffsims/tests/generators/test_rotation_list_generator.py:53-76 (every mesh x crystal system), checked
+    against the oracle instead of only being executed."""
+    from diffsims_b200.generators import sphere_mesh_generators as smg
+    from diffsims_b200.generators.rotation_list_generators import _points_to_grid, get_beam_directions_grid
+    for system in cases.BEAM_GRID_SYSTEMS:
+        if mesh == "random":   # unseeded in the reference: same vertices into both implementations
+            pts = smg.get_random_sphere_vertices(5, seed=17)
+            got = _points_to_grid(pts, system, want_quaternions=False)[0].cpu().numpy()
+            assert get_beam_directions_grid(system, 5, mesh=mesh).shape[1] == 3
+            ref = K.beam_directions_grid(system, 5, mesh=mesh, points=pts)
+        else:
+            got = get_beam_directions_grid(system, 5, mesh=mesh)
+            ref = K.beam_directions_grid(system, 5, mesh=mesh)
+        assert got.shape == ref.shape and got.shape[0] > 0
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10)
+
+
+def test_beam_directions_grid_to_euler():
+    """diffsims/tests/generators/test_sphere_mesh_generators.py:124-146."""
+    from diffsims_b200.generators.sphere_mesh_generators import beam_directions_grid_to_euler
+    grid = np.array([[1.0, 0, 0], [0, 1, 0], [0, 1, 1], [1, 0, 1]])
+    grid = (grid.T / np.linalg.norm(grid, axis=1)).T
+    np.testing.assert_allclose(beam_directions_grid_to_euler(grid), [[0, 90, 90], [0, 90, 0], [0, 45, 0], [0, 45, 90]],
+                               atol=1e-12)
+    pts = np.random.default_rng(4).normal(size=(1000, 3))
+    pts[0] = (0, 0, 1)       # pole: arccos(0 / 0) -> nan_to_num
+    pts[1] = (0, 0, -2)
+    np.testing.assert_allclose(beam_directions_grid_to_euler(pts), K.beam_directions_grid_to_euler(pts), atol=1e-10)
+
+
 def engine_simulate(gt, quat, gen):
     from diffsims_b200 import engine
     return engine.simulate(gt, quat, gen.wavelength, 0.01, 0.01, "lorentzian")

@@ -191,3 +191,10 @@ def test_beam_directions_grid_against_reference(golden_dir):
         if key.endswith("_5deg"):
             mesh, system = key[:-5].rsplit("_", 1)
             np.testing.assert_array_equal(K.beam_directions_grid(system, 5, mesh=mesh), gold[key])
+    # mesh vertices of sphere_mesh_generators.py (uv sphere :42-93, icosahedral :378-450, random :453-483)
+    np.testing.assert_array_equal(K.uv_sphere_mesh_vertices(7), gold["vertices_uv_sphere_7deg"])
+    np.testing.assert_array_equal(K.icosahedral_mesh_vertices(9), gold["vertices_icosahedral_9deg"])
+    np.testing.assert_array_equal(K.icosahedral_mesh_vertices(3), gold["vertices_icosahedral_3deg"])
+    np.testing.assert_array_equal(K.random_sphere_vertices(4, seed=3), gold["vertices_random_4deg_seed3"])
+    # diffsims/tests/generators/test_sphere_mesh_generators.py: shapes only
+    assert K.uv_sphere_mesh_vertices(10).shape[1] == 3 and K.icosahedral_mesh_vertices(10).shape[1] == 3
