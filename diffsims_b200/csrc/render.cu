@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         for (int e = threadIdx.x; e < 16 * p.n4; e += RN_THREADS) {
             const int copy = e / (4 * p.n4), rem = e % (4 * p.n4);
             const int a = (rem >> 2) * 4 + copy + (rem & 3);  // position in the padded kernel
-            const int k = abs(a - (p.radius + 8));
+            const int k = abs(a - (p.radius + LUT_PAD));
             lutf[e] = (k <= p.radius) ? (float)(exp(-0.5 / (p.sigma * p.sigma) * (double)k * (double)k) * inv) : 0.f;
         }
         __syncthreads();
@@ -346,26 +346,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                             for (int j = 0; j < 8; ++j) acc[i][j] = (acc[i][j] == vmax_all) ? 1.0f : acc[i][j] * sc;
                         sc = 1.0f;
                     }
-                    float *dst = img + (size_t)y0 * p.W + x0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool yok = y0 + i < p.H;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float *d = dst + (size_t)i * p.W + 32 * h;
-                            if (VEC) {
-                                if (yok && x0 + 32 * h < p.W)
-                                    __stcs(reinterpret_cast<float4 *>(d),
-                                           any ? make_float4(acc[i][4 * h] * sc, acc[i][4 * h + 1] * sc,
-                                                             acc[i][4 * h + 2] * sc, acc[i][4 * h + 3] * sc)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f));
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (yok && x0 + 32 * h + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
-                            }
-                        }
-                    }
+                    store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc);
                 }
             }
             if (!store) {
@@ -458,7 +439,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         int ts = 64;
         while (ts < 2 * cap) ts <<= 1;
         p.table_size = ts;
-        p.n4 = (2 * radius + 9 + 3) / 4 + 2;
+        p.n4 = lut_entries(radius);
         lut_bytes = (size_t)4 * p.n4 * 16;
         group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16);
     } else {

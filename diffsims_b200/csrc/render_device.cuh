@@ -13,6 +13,10 @@ constexpr int RN_WARPS = 8;
 constexpr int RN_THREADS = RN_WARPS * 32;
 constexpr int RN_RW = 64;  // warp region width  (8 lanes x 8 px)
 constexpr int RN_RH = 32;  // warp region height (4 lanes x 8 px)
+// Zero padding of the tap LUT on either side of the kernel support.  A spot that passes the region cull is at most
+// R + 31 pixels from any 4-pixel group of the region, so with 32 the hot loop needs no index clamp.
+constexpr int LUT_PAD = 32;
+inline int lut_entries(int radius) { return ((2 * radius + 2 * LUT_PAD + 3) >> 2) + 2; }
 
 struct RenderParams {
     int n_tmpl, cap, H, W;
@@ -60,12 +64,12 @@ __device__ __forceinline__ FastSmem carve_fast(unsigned char *base, const Render
 }
 
 
-// LUT layout.  The padded symmetric kernel is L[a] = w[|a - (R + 8)|] (0 outside the support).  Copy k
+// LUT layout.  The padded symmetric kernel is L[a] = w[|a - (R + LUT_PAD)|] (0 outside the support).  Copy k
 // (k = 0..3) holds float4 entries i -> (L[4i+k] .. L[4i+k+3]), so four consecutive taps at ANY integer
-// offset are one aligned LDS.128: offset d -> a = d + R + 8, copy a & 3, entry a >> 2 clamped to
+// offset are one aligned LDS.128: offset d -> a = d + R + LUT_PAD, copy a & 3, entry a >> 2 clamped to
 // [0, n4 - 1] (both end entries are all zero).  Lanes of a quarter warp read consecutive entries.
 __device__ __forceinline__ float4 fetch4(const float4 *lut, int n4, int R, int d) {
-    const int a = d + R + 8;
+    const int a = d + R + LUT_PAD;
     const int i = min(max(a >> 2, 0), n4 - 1);
     return lut[(a & 3) * n4 + i];
 }
@@ -125,14 +129,18 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 struct LutRef {
     uint32_t base;  // shared address of copy 0
     int n4, last;   // entries per copy, n4 - 1
-    int bias;       // R + 8
+    int bias;       // R + LUT_PAD
 };
-// taps L[a .. a+3] with a = offset + R + 8 already applied
+// taps L[a .. a+3] with a = offset + R + LUT_PAD already applied
 __device__ __forceinline__ float4 fetch4s(const LutRef &L, int a) {
     const int i = min(max(a >> 2, 0), L.last);
     return lds128(L.base + (uint32_t)(((a & 3) * L.n4 + i) << 4));
 }
-__device__ __forceinline__ float4 folded4s(const LutRef &L, int p0b /* p0 + R + 8 */, int c, int n, int R) {
+// shared address of the entry holding taps a .. a + 3, for a known to lie inside the padded table
+__device__ __forceinline__ uint32_t fetch_addr(const LutRef &L, int a) {
+    return L.base + (uint32_t)(((a & 3) * L.n4 + (a >> 2)) << 4);
+}
+__device__ __forceinline__ float4 folded4s(const LutRef &L, int p0b /* p0 + R + LUT_PAD */, int c, int n, int R) {
     float4 w = fetch4s(L, p0b - c);
     if (c < R) w = add4(w, fetch4s(L, p0b + c + 1));               // image at -c - 1
     if (c >= n - R) w = add4(w, fetch4s(L, p0b + c + 1 - 2 * n));  // image at 2n - 1 - c
@@ -152,7 +160,7 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
     L.base = smem_u32(s.lut);
     L.n4 = p.n4;
     L.last = p.n4 - 1;
-    L.bias = R + 8;
+    L.bias = R + LUT_PAD;
     const uint32_t spot_s = smem_u32(s.spot);
     const int xb = x0 + L.bias, yb = y0 + L.bias;
     bool any = false;
@@ -179,15 +187,18 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
             const int sx = spot_ix(r), sy = spot_iy(r);
             const float a = spot_amp(r);
             float4 ya, yb4;
+            uint32_t ay_s = 0;
+            const uint32_t ax_s = fetch_addr(L, xb - sx);  // column group h: + 8 entries
             if (WIDE) {
                 ya = folded4<true>(s.lut, p.n4, R, y0, sy, p.H);
                 yb4 = folded4<true>(s.lut, p.n4, R, y0 + 4, sy, p.H);
             } else if (spot_fold(r)) {  // the box crosses a border: add the reflect-folded images
                 ya = folded4s(L, yb, sy, p.H, R);
                 yb4 = folded4s(L, yb + 4, sy, p.H, R);
-            } else {
-                ya = fetch4s(L, yb - sy);
-                yb4 = fetch4s(L, yb + 4 - sy);
+            } else {  // in range by the cull above: no clamp; rows y0 + 4 .. + 7 are the next entry of the same copy
+                ay_s = fetch_addr(L, yb - sy);
+                ya = lds128(ay_s);
+                yb4 = lds128(ay_s + 16u);
             }
             const float wy[8] = {a * ya.x, a * ya.y, a * ya.z, a * ya.w, a * yb4.x, a * yb4.y, a * yb4.z, a * yb4.w};
 #pragma unroll
@@ -200,7 +211,7 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
                 else if (spot_fold(r))
                     xw = folded4s(L, xb + 32 * h, sx, p.W, R);
                 else
-                    xw = fetch4s(L, xb + 32 * h - sx);
+                    xw = lds128(ax_s + 128u * h);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     acc[i][4 * h + 0] = fmaf(wy[i], xw.x, acc[i][4 * h + 0]);
@@ -212,6 +223,57 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
         }
     }
     return any;
+}
+
+// Stream one finished warp region to the image (acc * sc, or zeros when no spot reached it) with evict-first
+// 16-byte stores: per store instruction a quarter warp covers 128 contiguous bytes of one row.  Regions
+// entirely inside the frame (all of them when H % 32 == 0 and W % 64 == 0) take a branch-free path.
+template <bool VEC>
+__device__ __forceinline__ void store_region(const RenderParams &p, float *img, int rx0, int ry0, int lane,
+                                             const float (&acc)[8][8], bool any, float sc) {
+    const int lx = lane & 7, ly = lane >> 3;
+    const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
+    float *dst = img + (size_t)y0 * p.W + x0;
+    if (VEC && ry0 + RN_RH <= p.H && rx0 + RN_RW <= p.W) {
+        float4 *d = reinterpret_cast<float4 *>(dst);
+        const int row4 = p.W >> 2;
+        if (!any) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                __stcs(d, z);
+                __stcs(d + 8, z);
+                d += row4;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                __stcs(d, make_float4(acc[i][0] * sc, acc[i][1] * sc, acc[i][2] * sc, acc[i][3] * sc));
+                __stcs(d + 8, make_float4(acc[i][4] * sc, acc[i][5] * sc, acc[i][6] * sc, acc[i][7] * sc));
+                d += row4;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool yok = y0 + i < p.H;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float *d = dst + (size_t)i * p.W + 32 * h;
+            if (VEC) {  // W % 4 == 0: a float4 group is entirely inside or outside the frame
+                if (yok && x0 + 32 * h < p.W)
+                    __stcs(reinterpret_cast<float4 *>(d),
+                           any ? make_float4(acc[i][4 * h] * sc, acc[i][4 * h + 1] * sc, acc[i][4 * h + 2] * sc,
+                                             acc[i][4 * h + 3] * sc)
+                               : make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (yok && x0 + 32 * h + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
         for (int e = threadIdx.x; e < 16 * p.n4; e += RN_THREADS) {
             const int copy = e / (4 * p.n4), rem = e % (4 * p.n4);
             const int a = (rem >> 2) * 4 + copy + (rem & 3);
-            const int k = abs(a - (p.radius + 8));
+            const int k = abs(a - (p.radius + LUT_PAD));
             lutf[e] = (k <= p.radius) ? (float)(exp(-0.5 / (p.sigma * p.sigma) * (double)k * (double)k) * inv) : 0.f;
         }
     }
@@ -303,7 +303,6 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                 float acc[8][8];
                 const bool any = accumulate_fast<false>(p, fs, n_live, rx0, ry0, lane, acc);
-                const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
                 float sc = any ? scale : 0.f;
                 if (n_pass == 2 && any && flags[reg]) {  // pin the maximum pixel to exactly 1 (see render.cu)
 #pragma unroll
@@ -312,26 +311,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                         for (int j = 0; j < 8; ++j) acc[i][j] = (acc[i][j] == vmax) ? 1.0f : acc[i][j] * sc;
                     sc = 1.0f;
                 }
-                float *dst = img + (size_t)y0 * p.W + x0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool yok = y0 + i < p.H;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float *d = dst + (size_t)i * p.W + 32 * h;
-                        if (VEC) {
-                            if (yok && x0 + 32 * h < p.W)
-                                __stcs(reinterpret_cast<float4 *>(d),
-                                       any ? make_float4(acc[i][4 * h] * sc, acc[i][4 * h + 1] * sc,
-                                                         acc[i][4 * h + 2] * sc, acc[i][4 * h + 3] * sc)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f));
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (yok && x0 + 32 * h + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
-                        }
-                    }
-                }
+                store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[slot]);
@@ -347,7 +327,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
 
 static int pipe_max_cap() {
     const char *e = getenv("DS_RENDER_PIPE_MAXCAP");
-    return e ? atoi(e) : 128;
+    return e ? atoi(e) : 512;  // beyond that (or when the slots do not fit in shared memory): render_kernel
 }
 
 // Returns 1 if the pipelined kernel was launched, 0 if the configuration is not eligible, < 0 on error.
@@ -358,14 +338,15 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     const int front_bytes = (int)((p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 + (size_t)p.cap * 8);
     // one front warp keeps up with the sparsest patterns; above 32 reflections per template two share the work
     int nf = p.cap <= 32 ? 1 : 2;
-    if (const char *e = getenv("DS_RENDER_FRONTS")) nf = atoi(e) == 2 ? 2 : 1;
+    if (const char *e = getenv("DS_RENDER_FRONTS")) nf = min(max(atoi(e), 1), 3);
     const size_t smem = (size_t)4 * p.n4 * 16 + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
     if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
-    void (*kern)(RenderParams, int, int) =
-        nf == 1 ? (vec ? render_pipe_kernel<true, 1> : render_pipe_kernel<false, 1>)
-                : (vec ? render_pipe_kernel<true, 2> : render_pipe_kernel<false, 2>);
-    static bool attr[4] = {false, false, false, false};
+    void (*const kerns[3][2])(RenderParams, int, int) = {{render_pipe_kernel<false, 1>, render_pipe_kernel<true, 1>},
+                                                         {render_pipe_kernel<false, 2>, render_pipe_kernel<true, 2>},
+                                                         {render_pipe_kernel<false, 3>, render_pipe_kernel<true, 3>}};
+    void (*kern)(RenderParams, int, int) = kerns[nf - 1][vec ? 1 : 0];
+    static bool attr[6] = {false, false, false, false, false, false};
     const int slot_id = (nf - 1) * 2 + (vec ? 1 : 0);
     if (smem > 48 * 1024 && !attr[slot_id]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

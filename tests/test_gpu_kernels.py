@@ -337,3 +337,31 @@ def test_render_slow_path_with_many_spots(eng):
         ref = K.diffraction_pattern(X[r, :cnt[r]], I[r, :cnt[r]], shape, sigma=2.5, calibration=1 / 64, fast=False,
                                     normalize=False, clip_threshold=1.0) if cnt[r] else np.zeros(shape)
         assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
+
+
+@pytest.mark.parametrize("pipe", ["1", "0"])
+@pytest.mark.parametrize("cap,sigma,normalize", [(288, 10.0, True), (288, 3.0, False), (512, 6.0, True),
+                                                  (1024, 2.0, True)])
+def test_render_fast_path_with_many_spots(eng, monkeypatch, pipe, cap, sigma, normalize):
+    """Dense patterns (hundreds of reflections per template) through both schedules: the warp-specialised kernel
+    takes capacities up to 512 while its slots fit in shared memory, render_kernel everything else."""
+    import torch
+    monkeypatch.setenv("DS_RENDER_PIPE", pipe)
+    rng = np.random.default_rng(cap)
+    n, shape = 5, (256, 256)
+    X = np.zeros((n, cap, 3))
+    X[..., :2] = rng.uniform(-1.05, 1.05, (n, cap, 2))     # some outside the frame
+    I = rng.uniform(1, 500, (n, cap))
+    cnt = np.array([cap, cap - 37, cap // 2 + 1, 1, 0], np.int32)
+    dev = eng.device()
+    out = eng.render(torch.as_tensor(cnt, device=dev), torch.as_tensor(X, device=dev), torch.as_tensor(I, device=dev),
+                     shape, sigma, 1 / 128, (127.5, 127.5), normalize=normalize).cpu().numpy()
+    for r in range(n):
+        if cnt[r] == 0:
+            assert not out[r].any()
+            continue
+        ref = K.diffraction_pattern(X[r, :cnt[r]], I[r, :cnt[r]], shape, sigma=sigma, calibration=1 / 128,
+                                    direct_beam_position=(127.5, 127.5), normalize=normalize)
+        assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
+        if normalize:
+            assert out[r].max() == 1.0
