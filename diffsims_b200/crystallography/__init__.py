@@ -75,7 +75,9 @@ class ReciprocalLatticeVector:
                 self._coordinate_format = "hkil"
             hkl = np.atleast_2d(np.asarray(hkl))
             data = hkl.astype(float) @ np.asarray(phase.structure.lattice.recbase).T
-        self.data = data.reshape(-1, 3)
+        # vectors are kept flat; N-D inputs are flattened in the order of orix `Object3d.flatten` (first axis fastest),
+        # which is what the reference's `to_flat_polar` sees (_diffracting_vector.py:186-194)
+        self.data = data.T.reshape(3, -1).T if data.ndim > 2 else data.reshape(-1, 3)
 
     @property
     def phase(self):

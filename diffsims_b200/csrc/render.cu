@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                         px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
                         py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
                         I = sint[j];
-                        if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
+                        // get_diffraction_pattern keeps the in-frame spots only (simulation2d.py:422-430); the bare
+                        // rasteriser also spreads spots lying outside the frame into it
+                        if (p.keep_outside || (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H)) {
                             inframe = true;
                             rad = sqrt(log(p.clip / (pref * I)) / ef);  // detector_functions.py:339
                             live = !isnan(rad);
@@ -234,10 +236,16 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                         ss.fy[d] = (float)py;
                         ss.amp[d] = (float)(I * pref);
                         // slices :343-352: [max(0, ceil(c - r)), min(n, floor(c + r + 1)))
-                        ss.xlo[d] = (short)max(0, (int)fmin(ceil(px - rad), 32000.0));
-                        ss.xhi[d] = (short)(min(p.W, (int)fmin(floor(px + rad + 1.0), 32000.0)) - 1);
-                        ss.ylo[d] = (short)max(0, (int)fmin(ceil(py - rad), 32000.0));
-                        ss.yhi[d] = (short)(min(p.H, (int)fmin(floor(py + rad + 1.0), 32000.0)) - 1);
+                        int x_stop = (int)fmax(fmin(floor(px + rad + 1.0), 32000.0), -32000.0);
+                        int y_stop = (int)fmax(fmin(floor(py + rad + 1.0), 32000.0), -32000.0);
+                        // a negative slice stop counts from the end (numpy / numba): only reachable for spots
+                        // outside the frame, i.e. through the bare function
+                        if (x_stop < 0) x_stop = max(x_stop + p.W, 0);
+                        if (y_stop < 0) y_stop = max(y_stop + p.H, 0);
+                        ss.xlo[d] = (short)max(0, (int)fmax(fmin(ceil(px - rad), 32000.0), -32000.0));
+                        ss.xhi[d] = (short)(min(p.W, x_stop) - 1);
+                        ss.ylo[d] = (short)max(0, (int)fmax(fmin(ceil(py - rad), 32000.0), -32000.0));
+                        ss.yhi[d] = (short)(min(p.H, y_stop) - 1);
                     }
                     n_live += __popc(mask);
                 }
@@ -429,6 +437,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.ticket = ticket;
     p.table_size = 0;
     p.n4 = 0;
+    DS_REQUIRE(fast >= 0 && fast <= 2, "ds_render: fast must be 0, 1 or 2");
+    p.keep_outside = (fast == 2);
+    if (fast == 2) fast = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     size_t lut_bytes = 0;
     int group_bytes;

@@ -30,6 +30,7 @@ struct RenderParams {
     int table_size;  // fast: hash slots (power of two)
     int n4;          // fast: float4 entries per shifted LUT copy
     int stage;       // 1: spot rows are prefetched into shared memory with cp.async.bulk (TMA engine)
+    int keep_outside;  // sub-pixel path: do not drop spots whose centre lies outside the frame
     float *images;
     int *ticket;  // [2] device scratch, zero on entry and on exit: dynamic template assignment
 };

@@ -124,10 +124,13 @@ int ds_simulate(void *stream,
  * Replaces Simulation2D._get_transformed_coordinates (diffsims/simulations/simulation2d.py:261-285),
  * the in-frame test / truncation / normalisation of get_diffraction_pattern (:357-442) and
  * get_pattern_from_pixel_coordinates_and_intensities (diffsims/pattern/detector_functions.py:251-311):
- *   fast != 0: integer pixels, last-write-wins assignment (:293-298) then scipy.ndimage.gaussian_filter
+ *   fast == 1: integer pixels, last-write-wins assignment (:293-298) then scipy.ndimage.gaussian_filter
  *              (separable, mode="reflect", taps exp(-k^2 / 2 sigma^2) / sum for |k| <= radius; the caller
  *              passes radius = int(truncate * sigma + 0.5), scipy's rule with truncate = 4);
- *   fast == 0: _subpixel_gaussian (:314-359), additive, clip box, no border folding.
+ *   fast == 0: _subpixel_gaussian (:314-359), additive, clip box, no border folding, for the spots inside the
+ *              frame (what get_diffraction_pattern passes on, simulation2d.py:422-430);
+ *   fast == 2: the same without the in-frame selection (the bare function: a spot centred outside the frame
+ *              still spreads into it).
  * (DiffractionSimulation.get_diffraction_pattern, diffsims/sims/diffraction_simulation.py:296-354, is the
  * same computation for square shapes: pattern[x, y] = I followed by .T.)
  * images[n_tmpl][H][W] float32.  Rows of xyz are [cap][3] doubles (z ignored).

@@ -98,6 +98,15 @@ def detector_spots(shape, n, seed):
     return xy, inten
 
 
+def detector_spots_outside(shape, n, seed):
+    """Float pixel coordinates partly outside the frame (the bare rasteriser spreads them into it; a negative
+    slice stop wraps around as in numpy) and integer coordinates with negative entries (index wrap)."""
+    rng = np.random.default_rng(seed)
+    xy = np.stack([rng.uniform(-8, shape[1] + 8, n), rng.uniform(-8, shape[0] + 8, n)], axis=1)
+    xy_int = np.stack([rng.integers(-shape[1], shape[1], n), rng.integers(-shape[0], shape[0], n)], axis=1)
+    return xy, xy_int, rng.uniform(20, 900, n)
+
+
 def random_eulers(n, seed):
     rng = np.random.default_rng(seed)
     e = np.stack([rng.uniform(0, 360, n), np.rad2deg(np.arccos(rng.uniform(-1, 1, n))),

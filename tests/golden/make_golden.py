@@ -72,6 +72,9 @@ for name, (shape, sigma, n, seed) in cases.DETECTOR_CASES.items():
         xy.astype(int), inten, shape, sigma)
     out[f"{name}_float"] = det.get_pattern_from_pixel_coordinates_and_intensities(
         xy, inten * 2000.0, shape, sigma, 1.0)
+xy, xy_int, inten = cases.detector_spots_outside((70, 90), 40, 5)
+out["outside_float"] = det.get_pattern_from_pixel_coordinates_and_intensities(xy, inten, (70, 90), 2.5)
+out["outside_int"] = det.get_pattern_from_pixel_coordinates_and_intensities(xy_int, inten, (70, 90), 2.5)
 np.savez_compressed(HERE / "detector.npz", **out)
 
 # ---------------------------------------------------------------- sim_utils

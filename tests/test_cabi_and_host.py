@@ -142,6 +142,30 @@ def test_reciprocal_lattice_vector_basics():
         rlv.rotate_with_basis(Rotation.random(2))
     r, t = rlv.to_flat_polar()
     np.testing.assert_allclose(r, np.hypot(rlv.data[:, 0], rlv.data[:, 1]))
+    # diffsims/tests/crystallography/test_diffracting_vector.py:10-18, :24-40, :47-75
+    fe = Phase("ferrite", space_group=229, structure=Structure([Atom("Fe", [0, 0, 0]), Atom("Fe", [.5, .5, .5])],
+                                                               Lattice(2.8665, 2.8665, 2.8665, 90, 90, 90)))
+    dv = DiffractingVector(fe, hkl=[[1, 1, 1], [2, 0, 0]], intensity=[1, 2])
+    assert dv.phase == fe and dv.shape == (2,) and dv.hkl.shape == (2, 3)
+    np.testing.assert_allclose(dv.intensity, [1, 2])
+    np.testing.assert_allclose(dv.basis_rotation.to_matrix(), np.eye(3)[None], atol=1e-15)
+    full = DiffractingVector.from_min_dspacing(fe, 1.5)
+    full.intensity = 1
+    assert isinstance(full.intensity, np.ndarray) and full[0:3].size == 3
+    np.testing.assert_allclose(full[0:3].intensity, np.ones(3))
+    with pytest.raises(ValueError):
+        full.intensity = [0, 1]
+    rot = Rotation.from_euler([[90, 90, 0]], degrees=True)
+    fe2 = fe.deepcopy()
+    fe2.structure.lattice.setLatPar(baserot=rot.to_matrix()[0])
+    plain = ReciprocalLatticeVector(fe, hkl=[[1, 1, 1], [2, 0, 0]])
+    np.testing.assert_allclose(DiffractingVector(fe2, xyz=plain.data @ rot.to_matrix()[0]).hkl, plain.hkl, atol=1e-12)
+    r, t = DiffractingVector(fe, xyz=[[1, 1, 1], [0.5, -0.5, 0]]).to_flat_polar()
+    np.testing.assert_allclose(r, [np.sqrt(2), 0.70710678])
+    np.testing.assert_allclose(t, [np.pi / 4, -np.pi / 4])
+    r, t = DiffractingVector(fe, xyz=[[[1, 1, 1], [0.5, -0.5, 0]], [[1, 1, 1], [0.5, -0.5, 0]]]).to_flat_polar()
+    np.testing.assert_allclose(r, [np.sqrt(2), np.sqrt(2), 0.70710678, 0.70710678])
+    np.testing.assert_allclose(t, [np.pi / 4, np.pi / 4, -np.pi / 4, -np.pi / 4])
 
 
 # ------------------------------------------------------------------ Simulation2D container

@@ -531,3 +531,62 @@ def test_polar_flatten_user_built_simulations():
     p2.name = "al2"
     mp = Simulation2D(phases=[al, p2], simulation_generator=gen, coordinates=[[c4] * 4, [c4] * 4], rotations=[rot4, rot4])
     assert mp.polar_flatten_simulations()[0].shape == (8, 4)
+
+
+class TestGetPatternFromPixelCoordinatesAndIntensities:
+    """diffsims/tests/patterns/test_detector_functions.py:160-300, plus the oracle on random spots."""
+
+    @staticmethod
+    def f(*a, **k):
+        from diffsims_b200.pattern.detector_functions import get_pattern_from_pixel_coordinates_and_intensities
+        return get_pattern_from_pixel_coordinates_and_intensities(*a, **k)
+
+    def test_2d_vs_3d_coordinates(self):
+        c2 = np.asarray([[10, 10], [20, 30], [15, 20]])
+        c3 = np.asarray([[10, 10, 92], [20, 30, 0], [15, 20, -192]])
+        assert np.array_equal(self.f(c2, np.ones(3) * 100, (50, 50), 1), self.f(c3, np.ones(3) * 100, (50, 50), 1))
+
+    def test_integer_vs_float_coordinates(self):
+        ci = np.asarray([[10, 10], [20, 30], [15, 20]]).astype(int)
+        pi = self.f(ci, np.ones(3) * 100, (50, 50), 1).astype(int)
+        pf = self.f(ci.astype(float), np.ones(3) * 100, (50, 50), 1).astype(int)
+        assert np.allclose(pi, pf)
+
+    def test_low_intensity(self):
+        ci = np.asarray([[10, 10], [20, 30], [15, 20]]).astype(float)
+        assert np.sum(self.f(ci, np.ones(3), (50, 50), 1)) == 0.0
+
+    def test_total_intensity_preservation(self):
+        p = self.f(np.asarray([[10, 10]]).astype(int), np.array([100]), (50, 50), 3)
+        assert np.allclose(np.sum(p), 100)
+        ci = np.asarray([[10, 10]]).astype(float)
+        assert np.sum(self.f(ci, np.array([1000]), (50, 50), 1)) / 1000 > 0.999
+        assert np.sum(self.f(ci, np.array([20]), (50, 50), 1, clip_threshold=0.01)) / 20 > 0.999
+
+    def test_spot_in_corner(self):
+        ci = np.asarray([[0.3, 0.1]])
+        assert np.sum(self.f(ci, np.array([100]), (50, 50), 3)) < 100
+        assert np.allclose(np.sum(self.f(ci.astype(int), np.array([100]), (50, 50), 3)), 100)
+
+    @pytest.mark.parametrize("integer", [True, False])
+    def test_matches_oracle(self, integer):
+        rng = np.random.default_rng(5)
+        shape = (70, 90)
+        xy = rng.uniform(-6, 96, (40, 2))          # floats may lie outside the frame and still spread into it
+        inten = rng.uniform(20, 900, 40)
+        if integer:
+            xy = np.stack([rng.integers(-90, 90, 40), rng.integers(-70, 70, 40)], axis=1)   # negative: numpy wrap
+        got = self.f(xy, inten, shape, 2.5)
+        ref = K.pattern_from_pixel_coordinates_and_intensities(xy, inten, shape, 2.5)
+        assert got.dtype == np.float64 and got.shape == shape
+        assert np.abs(got - ref).max() <= 1e-4 * ref.max()
+        if integer:
+            with pytest.raises(IndexError):
+                self.f(np.array([[95, 3]]), np.array([1.0]), shape, 2.5)
+
+    def test_spots_outside_the_frame_match_reference_golden(self, golden_dir):
+        gold = np.load(golden_dir / "detector.npz")
+        xy, xy_int, inten = cases.detector_spots_outside((70, 90), 40, 5)
+        for coords, key in ((xy, "outside_float"), (xy_int, "outside_int")):
+            got = self.f(coords, inten, (70, 90), 2.5)
+            assert np.abs(got - gold[key]).max() <= 1e-4 * gold[key].max()

@@ -132,6 +132,16 @@ def test_rasteriser_against_reference(g, name):
         g["detector"][f"{name}_float"], rtol=1e-12, atol=1e-15)
 
 
+def test_rasteriser_spots_outside_the_frame_against_reference(g):
+    """The bare function spreads out-of-frame float spots into the frame (incl. numpy's wrap of a negative slice
+    stop) and wraps negative integer indices."""
+    xy, xy_int, inten = cases.detector_spots_outside((70, 90), 40, 5)
+    np.testing.assert_allclose(K.pattern_from_pixel_coordinates_and_intensities(xy, inten, (70, 90), 2.5),
+                               g["detector"]["outside_float"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(K.pattern_from_pixel_coordinates_and_intensities(xy_int, inten, (70, 90), 2.5),
+                               g["detector"]["outside_int"], rtol=1e-12, atol=1e-15)
+
+
 @pytest.mark.parametrize("name", list(cases.STRUCTURES))
 def test_intensities_against_reference(g, name):
     hkl = cases.hkl_box(3)
