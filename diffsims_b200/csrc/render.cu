@@ -53,7 +53,12 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
     // ---- CTA-wide, once: the 4-way shifted LUT of the normalised 1-D taps --------------------------------
     // scipy.ndimage._gaussian_kernel1d: exp(-0.5 k^2 / sigma^2) / sum over |k| <= radius
     float4 *lut = reinterpret_cast<float4 *>(smem_raw);
-    unsigned char *gbase = smem_raw + (FAST ? (size_t)4 * p.n4 * sizeof(float4) : 0) + (size_t)group * group_bytes;
+    unsigned char *gbase =
+        smem_raw + (FAST ? lut_smem_bytes(p.n4) + (size_t)p.hits_bytes : 0) + (size_t)group * group_bytes;
+    const uint32_t hits_s = (FAST && p.hits_bytes)
+                                ? smem_u32(smem_raw + lut_smem_bytes(p.n4)) +
+                                      (uint32_t)(warp * (p.hits_bytes / RN_WARPS))
+                                : 0u;
     if (FAST) {
         if (warp == 0) {
             double part = 0.0;
@@ -64,14 +69,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
             if (lane == 0) s_norm = part;
         }
         __syncthreads();
-        const double inv = 1.0 / s_norm;
-        float *lutf = reinterpret_cast<float *>(lut);
-        for (int e = threadIdx.x; e < 16 * p.n4; e += RN_THREADS) {
-            const int copy = e / (4 * p.n4), rem = e % (4 * p.n4);
-            const int a = (rem >> 2) * 4 + copy + (rem & 3);  // position in the padded kernel
-            const int k = abs(a - (p.radius + LUT_PAD));
-            lutf[e] = (k <= p.radius) ? (float)(exp(-0.5 / (p.sigma * p.sigma) * (double)k * (double)k) * inv) : 0.f;
-        }
+        fill_lut(lut, p.n4, p.radius, p.sigma, 1.0 / s_norm, threadIdx.x, RN_THREADS);
         __syncthreads();
     }
     const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
@@ -115,8 +113,6 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
         bulk_g2s(stage[buf], p.xyz + (size_t)t * p.cap * 3, bx, &s_bar[group][buf]);
         bulk_g2s(stage[buf] + p.cap * 3, p.intensity + (size_t)t * p.cap, bi, &s_bar[group][buf]);
     };
-
-    const int lx = lane & 7, ly = lane >> 3;
 
     // Templates are handed out by a global ticket, not by a static grid stride: per-SM write bandwidth is
     // not uniform on B200 and a static split leaves the fast SMs idle at the end (measured with
@@ -316,33 +312,17 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                 if (!store && !flags[reg]) continue;
                 const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                 float acc[8][8];
-                bool any;
+                bool any, mma = false;
                 if (FAST)
-                    any = accumulate_fast<WIDE>(p, fs, n_live, rx0, ry0, lane, acc);
+                    any = accumulate_region<WIDE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
                 else
                     any = accumulate_slow(p, ss, n_live, rx0, ry0, lane, acc);
-                const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
                 if (!store) {
                     if (!any) {  // no spot reaches the region: all its pixels are exactly 0
                         vmax = fmaxf(vmax, 0.f);
                         continue;
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool yok = y0 + i < p.H;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (VEC) {  // W % 4 == 0: a float4 group is entirely inside or outside the frame
-                                const float m4 = fmaxf(fmaxf(acc[i][4 * h], acc[i][4 * h + 1]),
-                                                       fmaxf(acc[i][4 * h + 2], acc[i][4 * h + 3]));
-                                if (yok && x0 + 32 * h < p.W) vmax = fmaxf(vmax, m4);
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (yok && x0 + 32 * h + q < p.W) vmax = fmaxf(vmax, acc[i][4 * h + q]);
-                            }
-                        }
-                    }
+                    vmax = fmaxf(vmax, region_max<VEC>(p, rx0, ry0, lane, acc, mma));
                 } else {
                     float sc = any ? scale : 0.f;
                     // numpy divides: the maximum pixel is exactly 1.  acc * (1 / max) can be 1 ulp off, so the
@@ -354,7 +334,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                             for (int j = 0; j < 8; ++j) acc[i][j] = (acc[i][j] == vmax_all) ? 1.0f : acc[i][j] * sc;
                         sc = 1.0f;
                     }
-                    store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc);
+                    store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc, mma);
                 }
             }
             if (!store) {
@@ -437,6 +417,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.ticket = ticket;
     p.table_size = 0;
     p.n4 = 0;
+    p.hits_bytes = 0;
+    p.mma_min = MMA_MIN_HITS;
+    p.mma_tmpl_min = 1 << 30;
     DS_REQUIRE(fast >= 0 && fast <= 2, "ds_render: fast must be 0, 1 or 2");
     p.keep_outside = (fast == 2);
     if (fast == 2) fast = 0;
@@ -451,7 +434,19 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         while (ts < 2 * cap) ts <<= 1;
         p.table_size = ts;
         p.n4 = lut_entries(radius);
-        lut_bytes = (size_t)4 * p.n4 * 16;
+        // per-warp hit lists of the tensor-core path for dense regions (DS_RENDER_MMA=0 switches it off)
+        p.hits_bytes = 0;
+        if (!wide && cap >= MMA_MIN_HITS && cap <= 4096 && !(getenv("DS_RENDER_MMA") && atoi(getenv("DS_RENDER_MMA")) == 0))
+            p.hits_bytes = RN_WARPS * ((2 * cap * 2 + 15) & ~15);  // 2 cap entries: spots + their reflect images
+        p.mma_min = MMA_MIN_HITS;
+        if (const char *e = getenv("DS_RENDER_MMA_MIN")) p.mma_min = atoi(e) > 1 ? atoi(e) : MMA_MIN_HITS;
+        {   // a region is reached by about this fraction of a template's spots; templates expected to put fewer
+            // than mma_min spots into a region skip the hit lists altogether
+            const double frac = fmin(1.0, (2.0 * radius + 1 + RN_RW) * (2.0 * radius + 1 + RN_RH) / ((double)W * H));
+            p.mma_tmpl_min = (int)ceil(p.mma_min / frac);
+            if (const char *e = getenv("DS_RENDER_MMA_TMPL_MIN")) p.mma_tmpl_min = atoi(e);
+        }
+        lut_bytes = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes;
         group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16);
     } else {
         group_bytes = (int)slow_smem_bytes(cap);

@@ -3,6 +3,8 @@
 #pragma once
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ds {
@@ -14,9 +16,12 @@ constexpr int RN_THREADS = RN_WARPS * 32;
 constexpr int RN_RW = 64;  // warp region width  (8 lanes x 8 px)
 constexpr int RN_RH = 32;  // warp region height (4 lanes x 8 px)
 // Zero padding of the tap LUT on either side of the kernel support.  A spot that passes the region cull is at most
-// R + 31 pixels from any 4-pixel group of the region, so with 32 the hot loop needs no index clamp.
-constexpr int LUT_PAD = 32;
+// R + 63 pixels from any pixel of the region (R + 31 within a culled 32-px column group), so with 64 the hot
+// loops need no index clamp.
+constexpr int LUT_PAD = 64;
 inline int lut_entries(int radius) { return ((2 * radius + 2 * LUT_PAD + 3) >> 2) + 2; }
+// shared bytes of the tap tables: four shifted float copies (n4 float4 each) + the packed bf16 hi|lo table
+__host__ __device__ inline size_t lut_smem_bytes(int n4) { return (size_t)5 * n4 * 16; }
 
 struct RenderParams {
     int n_tmpl, cap, H, W;
@@ -31,6 +36,9 @@ struct RenderParams {
     int n4;          // fast: float4 entries per shifted LUT copy
     int stage;       // 1: spot rows are prefetched into shared memory with cp.async.bulk (TMA engine)
     int keep_outside;  // sub-pixel path: do not drop spots whose centre lies outside the frame
+    int hits_bytes;    // fast path: bytes of the per-warp hit lists behind the LUT (0 = tensor-core path off)
+    int mma_min;       // spots per region from which the tensor-core path is taken
+    int mma_tmpl_min;  // spots per template from which regions are examined for it
     float *images;
     int *ticket;  // [2] device scratch, zero on entry and on exit: dynamic template assignment
 };
@@ -79,6 +87,29 @@ __device__ __forceinline__ float tap(const float4 *lut, int n4, int R, int d) { 
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// Fill the tap tables (all threads of the CTA; `inv_norm` = 1 / sum of the unnormalised taps):
+//   floats [0, 16 n4):        the four shifted copies described above (copy 0 is the flat padded kernel L[a]);
+//   words  [16 n4, 20 n4):    L[a] split for the tensor-core path, bf16(L) in the low half and
+//                             bf16(L - bf16(L)) in the high half.
+__device__ __forceinline__ void fill_lut(float4 *lut, int n4, int radius, double sigma, double inv_norm, int tid,
+                                         int n_threads) {
+    float *lutf = reinterpret_cast<float *>(lut);
+    uint32_t *hl = reinterpret_cast<uint32_t *>(lutf + 16 * n4);
+    for (int e = tid; e < 20 * n4; e += n_threads) {
+        const int copy = e / (4 * n4), rem = e % (4 * n4);
+        const int a = (copy < 4) ? (rem >> 2) * 4 + copy + (rem & 3) : rem;  // position in the padded kernel
+        const int k = abs(a - (radius + LUT_PAD));
+        const float w = (k <= radius) ? (float)(exp(-0.5 / (sigma * sigma) * (double)k * (double)k) * inv_norm) : 0.f;
+        if (copy < 4) {
+            lutf[e] = w;
+        } else {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+            hl[rem] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        }
+    }
 }
 
 // Folded weights of 4 consecutive pixels p0..p0+3 for a delta at pixel `c` on an axis of length n:
@@ -226,18 +257,272 @@ __device__ __forceinline__ bool accumulate_fast(const RenderParams &p, const Fas
     return any;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Dense patterns: a region reached by S spots is the rank-S product  out[y][x] = sum_s (a_s Wy_s[y]) Wx_s[x],
+// i.e. a (32 x S) x (S x 64) matrix product.  From MMA_MIN_HITS spots per region on it runs on the tensor cores
+// (mma.sync m16n8k16, bf16 inputs, float32 accumulation): both operands are split into bf16 high and low parts
+// and three products (hi hi + hi lo + lo hi) keep ~16 mantissa bits, 2e-5 relative, inside the 1e-4-of-peak
+// parity bound.  Sparse regions keep the exact float32 FMA path above.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MMA_MIN_HITS = 16;
+
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+// (v0, v1) -> packed bf16 pairs hi and lo with v ~= hi + lo; v0 in the low half (the smaller k index)
+__device__ __forceinline__ void bf16_split2(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+    const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void mma_bf16(float &c0, float &c1, float &c2, float &c3, const uint32_t (&a)[4],
+                                         uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// Accumulate one warp region; `mma` reports the register layout of the result (see acc_coords).
+// hits_s: shared address of this warp's hit list (uint16 [hits_cap]) or 0 when the tensor-core path is off.
+//
+// Hit-list entry: spot index (12 bits) | x image << 12 | y image << 14.  scipy's mode="reflect" is the sum of
+// the direct delta at c and its mirror images at -c - 1 (image 1, spots within R of the low border) and
+// 2n - 1 - c (image 2, high border); an image is listed only for regions it reaches, as one more rank-1 term,
+// so every tap of the matrix operands is a single table read.
+template <bool WIDE>
+__device__ __forceinline__ bool accumulate_region(const RenderParams &p, const FastSmem &s, int n_live, int rx0,
+                                                  int ry0, int lane, float (&acc)[8][8], uint32_t hits_s, bool &mma) {
+    mma = false;
+    // (the template-level threshold keeps the list building away from patterns too sparse to fill a chunk)
+    if (WIDE || hits_s == 0u || n_live < p.mma_tmpl_min) return accumulate_fast<WIDE>(p, s, n_live, rx0, ry0, lane, acc);
+    const int R = p.radius;
+    const uint32_t spot_s = smem_u32(s.spot);
+    const int hits_cap = (p.hits_bytes / RN_WARPS) >> 1;
+    // ---- the spots (and mirror images) whose box reaches the region, in list order
+    int n_hits = 0;
+    for (int base = 0; base < n_live; base += 32) {
+        const int j = base + lane;
+        unsigned mx = 0, my = 0;  // bit k: image k of this spot reaches the region
+        if (j < n_live) {
+            const uint2 r = lds64(spot_s + 8u * j);
+            const int sx = spot_ix(r), sy = spot_iy(r);
+            if (sx + R >= rx0 && sx - R < rx0 + RN_RW && sy + R >= ry0 && sy - R < ry0 + RN_RH) {
+                mx = 1u | ((sx < R && rx0 <= R - 1 - sx) ? 2u : 0u) |
+                     ((sx >= p.W - R && rx0 + RN_RW - 1 >= 2 * p.W - 1 - sx - R) ? 4u : 0u);
+                my = 1u | ((sy < R && ry0 <= R - 1 - sy) ? 2u : 0u) |
+                     ((sy >= p.H - R && ry0 + RN_RH - 1 >= 2 * p.H - 1 - sy - R) ? 4u : 0u);
+            }
+        }
+        const int mine = __popc(mx) * __popc(my);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        if (n_hits + total > hits_cap) {  // (cannot happen below ~half the capacity in border spots)
+            n_hits = -1;
+            break;
+        }
+        int at = n_hits + incl - mine;
+        for (unsigned by = my; by; by &= by - 1)
+            for (unsigned bx = mx; bx; bx &= bx - 1)
+                sts16(hits_s + 2u * (uint32_t)at++,
+                      (unsigned)j | ((unsigned)(__ffs(bx) - 1) << 12) | ((unsigned)(__ffs(by) - 1) << 14));
+        n_hits += total;
+    }
+    __syncwarp();
+    if (n_hits < p.mma_min) return accumulate_fast<false>(p, s, n_live, rx0, ry0, lane, acc);
+    mma = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t lut0 = smem_u32(s.lut);                  // copy 0: the flat padded kernel L[a]
+    const uint32_t lut_hl = lut0 + 64u * (uint32_t)p.n4;    // packed bf16 hi | lo of L[a]
+    const int bias = R + LUT_PAD;
+    // pixel of B column g in tile 0 and of A row g in tile 0, with the table bias folded in
+    const int xb = rx0 + 4 * (g >> 1) + (g & 1) + bias, yb = ry0 + g + bias;
+    for (int k0 = 0; k0 < n_hits; k0 += 16) {
+        // this lane's four terms of the chunk: k = 2t, 2t + 1, 2t + 8, 2t + 9 (the fragment layout of m16n8k16);
+        // the tail is padded with zero-amplitude terms
+        uint32_t ax_s[4], ay_s[4];
+        float amp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = k0 + 2 * t + (j & 1) + 8 * (j >> 1);
+            int cx = rx0, cy = ry0;
+            amp[j] = 0.f;
+            if (kk < n_hits) {
+                const unsigned e = lds16(hits_s + 2u * (uint32_t)kk);
+                const uint2 r = lds64(spot_s + 8u * (e & 0xfffu));
+                const int sx = spot_ix(r), sy = spot_iy(r);
+                const unsigned ix = (e >> 12) & 3u, iy = e >> 14;
+                cx = ix == 0u ? sx : (ix == 1u ? -sx - 1 : 2 * p.W - 1 - sx);
+                cy = iy == 0u ? sy : (iy == 1u ? -sy - 1 : 2 * p.H - 1 - sy);
+                amp[j] = spot_amp(r);
+            }
+            ax_s[j] = lut_hl + 4u * (uint32_t)(xb - cx);
+            ay_s[j] = lut0 + 4u * (uint32_t)(yb - cy);
+        }
+        // A = a_s Wy_s[y]: rows g, g + 8 of the two 16-row tiles
+        uint32_t a_hi[2][4], a_lo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = amp[j] * lds32f(ay_s[j] + 4u * (uint32_t)(16 * mt + 8 * r));
+                bf16_split2(v[0], v[1], a_hi[mt][r], a_lo[mt][r]);
+                bf16_split2(v[2], v[3], a_hi[mt][2 + r], a_lo[mt][2 + r]);
+            }
+        // B = Wx_s[x], one 8-column tile at a time; column g of tile nt is pixel 16 (nt >> 1) + 4 (g >> 1) +
+        // 2 (nt & 1) + (g & 1), which makes a lane's C columns of a tile pair four consecutive pixels
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = lds32u(ax_s[j] + 4u * (uint32_t)(16 * (nt >> 1) + 2 * (nt & 1)));
+            const uint32_t b_hi0 = prmt(w[0], w[1], 0x5410u), b_lo0 = prmt(w[0], w[1], 0x7632u);
+            const uint32_t b_hi1 = prmt(w[2], w[3], 0x5410u), b_lo1 = prmt(w[2], w[3], 0x7632u);
+            // three products per tile, issued so that consecutive MMAs never share an accumulator
+            const int i0 = nt >> 1, i1 = 4 + (nt >> 1), jb = (nt & 1) * 2;
+            mma_bf16(acc[i0][jb], acc[i0][jb + 1], acc[i0][jb + 4], acc[i0][jb + 5], a_hi[0], b_hi0, b_hi1);
+            mma_bf16(acc[i1][jb], acc[i1][jb + 1], acc[i1][jb + 4], acc[i1][jb + 5], a_hi[1], b_hi0, b_hi1);
+            mma_bf16(acc[i0][jb], acc[i0][jb + 1], acc[i0][jb + 4], acc[i0][jb + 5], a_hi[0], b_lo0, b_lo1);
+            mma_bf16(acc[i1][jb], acc[i1][jb + 1], acc[i1][jb + 4], acc[i1][jb + 5], a_hi[1], b_lo0, b_lo1);
+            mma_bf16(acc[i0][jb], acc[i0][jb + 1], acc[i0][jb + 4], acc[i0][jb + 5], a_lo[0], b_hi0, b_hi1);
+            mma_bf16(acc[i1][jb], acc[i1][jb + 1], acc[i1][jb + 4], acc[i1][jb + 5], a_lo[1], b_hi0, b_hi1);
+        }
+    }
+    return true;
+}
+
+// Register layouts of a warp region's 64 x 32 pixels (acc[8][8] per lane):
+//   LAYOUT_SCALAR  lane (lx = lane & 7, ly = lane >> 3) holds rows ry0 + 8 ly + i, columns
+//                  rx0 + 4 lx + (j & 3) + 32 (j >> 2);
+//   LAYOUT_MMA     lane (g = lane >> 2, t = lane & 3) holds, in acc[i] with mt = i >> 2, pr = i & 3,
+//                  row ry0 + 16 mt + g (j < 4) or that + 8 (j >= 4), columns rx0 + 16 pr + 4 t + (j & 3)
+//                  -- the C fragments of mma.m16n8k16 with the column permutation chosen so that a lane
+//                  owns four consecutive pixels;
+//   LAYOUT_MMA_ST  LAYOUT_MMA after lanes g and g ^ 1 have swapped half of their tiles (mma_to_store_layout):
+//                  acc[i] with mt = i >> 2, ph = (i >> 1) & 1, sb = i & 1 is row ry0 + 16 mt + (g & ~1) + sb
+//                  (+ 8 for j >= 4), columns rx0 + 16 (2 ph + (g & 1)) + 4 t + (j & 3), so that a store
+//                  instruction covers 128 contiguous bytes of 4 rows like the scalar layout does.
+enum { LAYOUT_SCALAR = 0, LAYOUT_MMA = 1, LAYOUT_MMA_ST = 2 };
+
+__device__ __forceinline__ void acc_coords(int layout, int lane, int i, int j, int &row, int &col) {
+    if (layout == LAYOUT_MMA) {
+        row = 16 * (i >> 2) + (lane >> 2) + 8 * (j >> 2);
+        col = 16 * (i & 3) + 4 * (lane & 3) + (j & 3);
+    } else if (layout == LAYOUT_MMA_ST) {
+        const int g = lane >> 2;
+        row = 16 * (i >> 2) + (g & ~1) + (i & 1) + 8 * (j >> 2);
+        col = 16 * (2 * ((i >> 1) & 1) + (g & 1)) + 4 * (lane & 3) + (j & 3);
+    } else {
+        row = 8 * (lane >> 3) + i;
+        col = 4 * (lane & 7) + (j & 3) + 32 * (j >> 2);
+    }
+}
+
+// LAYOUT_MMA -> LAYOUT_MMA_ST: even-g lanes hand their odd column tiles to lane ^ 4 and receive its even ones.
+__device__ __forceinline__ void mma_to_store_layout(float (&acc)[8][8], int lane) {
+    const bool odd = (lane >> 2) & 1;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            const int ia = mt * 4 + 2 * ph, ib = ia + 1;  // column tiles 2 ph and 2 ph + 1 of this lane's rows
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float give = odd ? acc[ia][j] : acc[ib][j];
+                const float got = __shfl_xor_sync(0xffffffffu, give, 4);
+                // even lane: keeps tile 2 ph of its own row (slot 0), gets tile 2 ph of row g + 1 (slot 1)
+                // odd lane:  gets tile 2 ph + 1 of row g - 1 (slot 0), keeps tile 2 ph + 1 of its own row (slot 1)
+                if (odd)
+                    acc[ia][j] = got;
+                else
+                    acc[ib][j] = got;
+            }
+        }
+}
+
+// Largest in-frame pixel of a finished region.
+template <bool VEC>
+__device__ __forceinline__ float region_max(const RenderParams &p, int rx0, int ry0, int lane,
+                                            const float (&acc)[8][8], bool mma) {
+    const int layout = mma ? LAYOUT_MMA : LAYOUT_SCALAR;
+    float m = -INFINITY;
+    if (ry0 + RN_RH <= p.H && rx0 + RN_RW <= p.W) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; j += 4)
+                m = fmaxf(m, fmaxf(fmaxf(acc[i][j], acc[i][j + 1]), fmaxf(acc[i][j + 2], acc[i][j + 3])));
+        return m;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int row, col;
+            acc_coords(layout, lane, i, j, row, col);
+            if (ry0 + row < p.H && rx0 + col < p.W) m = fmaxf(m, acc[i][j]);
+        }
+    return m;
+}
+
 // Stream one finished warp region to the image (acc * sc, or zeros when no spot reached it) with evict-first
-// 16-byte stores: per store instruction a quarter warp covers 128 contiguous bytes of one row.  Regions
-// entirely inside the frame (all of them when H % 32 == 0 and W % 64 == 0) take a branch-free path.
+// 16-byte stores: per store instruction a quarter warp covers 128 contiguous bytes of one row (scalar layout;
+// 64 bytes in the tensor layout).  Regions entirely inside the frame (all of them when H % 32 == 0 and
+// W % 64 == 0) take a branch-free path.
 template <bool VEC>
 __device__ __forceinline__ void store_region(const RenderParams &p, float *img, int rx0, int ry0, int lane,
-                                             const float (&acc)[8][8], bool any, float sc) {
-    const int lx = lane & 7, ly = lane >> 3;
-    const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
-    float *dst = img + (size_t)y0 * p.W + x0;
+                                             float (&acc)[8][8], bool any, float sc, bool mma) {
+    if (mma) mma_to_store_layout(acc, lane);
+    const int layout = mma ? LAYOUT_MMA_ST : LAYOUT_SCALAR;
     if (VEC && ry0 + RN_RH <= p.H && rx0 + RN_RW <= p.W) {
-        float4 *d = reinterpret_cast<float4 *>(dst);
         const int row4 = p.W >> 2;
+        if (mma) {
+            int row, col;
+            acc_coords(LAYOUT_MMA_ST, lane, 0, 0, row, col);
+            float4 *d = reinterpret_cast<float4 *>(img + (size_t)(ry0 + row) * p.W + rx0 + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // acc[i]: 16 rows down per mt, 32 columns right per ph, one row down per sb
+                float4 *q = d + (size_t)(16 * (i >> 2) + (i & 1)) * row4 + 8 * ((i >> 1) & 1);
+                __stcs(q, make_float4(acc[i][0] * sc, acc[i][1] * sc, acc[i][2] * sc, acc[i][3] * sc));
+                __stcs(q + (size_t)8 * row4, make_float4(acc[i][4] * sc, acc[i][5] * sc, acc[i][6] * sc, acc[i][7] * sc));
+            }
+            return;
+        }
+        float4 *d = reinterpret_cast<float4 *>(img + (size_t)(ry0 + 8 * (lane >> 3)) * p.W + rx0 + 4 * (lane & 7));
         if (!any) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -257,13 +542,16 @@ __device__ __forceinline__ void store_region(const RenderParams &p, float *img, 
         return;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool yok = y0 + i < p.H;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float *d = dst + (size_t)i * p.W + 32 * h;
+            int row, col;
+            acc_coords(layout, lane, i, 4 * h, row, col);
+            const int y = ry0 + row, x = rx0 + col;
+            if (y >= p.H) continue;
+            float *d = img + (size_t)y * p.W + x;
             if (VEC) {  // W % 4 == 0: a float4 group is entirely inside or outside the frame
-                if (yok && x0 + 32 * h < p.W)
+                if (x < p.W)
                     __stcs(reinterpret_cast<float4 *>(d),
                            any ? make_float4(acc[i][4 * h] * sc, acc[i][4 * h + 1] * sc, acc[i][4 * h + 2] * sc,
                                              acc[i][4 * h + 3] * sc)
@@ -271,10 +559,9 @@ __device__ __forceinline__ void store_region(const RenderParams &p, float *img, 
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (yok && x0 + 32 * h + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
+                    if (x + q < p.W) d[q] = any ? acc[i][4 * h + q] * sc : 0.f;
             }
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
     // ---- shared memory: LUT | front workspace (stage x2, hash, key, inten) | slots ------------------------
     float4 *lut = reinterpret_cast<float4 *>(smem_raw);
     const int front = warp < NF ? warp : 0;
-    unsigned char *base = smem_raw + (size_t)4 * p.n4 * sizeof(float4) + (size_t)front * front_bytes;
+    const size_t shared_prefix = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes;  // LUT | hit lists
+    const uint32_t hits_s =
+        p.hits_bytes ? smem_u32(smem_raw + lut_smem_bytes(p.n4)) + (uint32_t)(warp * (p.hits_bytes / RN_WARPS)) : 0u;
+    unsigned char *base = smem_raw + shared_prefix + (size_t)front * front_bytes;
     uint64_t *s_stage = s_stage_all[front];
     double *stage[2] = {nullptr, nullptr};
     if (p.stage) {
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
     int *key = reinterpret_cast<int *>(base);
     base += (size_t)p.cap * 4;
     float *inten = reinterpret_cast<float *>(base);
-    base = smem_raw + (size_t)4 * p.n4 * sizeof(float4) + (size_t)NF * front_bytes;
+    base = smem_raw + shared_prefix + (size_t)NF * front_bytes;
     unsigned char *slots = base;
     auto slot_header = [&](int s) { return reinterpret_cast<PipeHeader *>(slots + (size_t)s * slot_bytes); };
     auto slot_spots = [&](int s) { return reinterpret_cast<uint2 *>(slots + (size_t)s * slot_bytes + 32); };
@@ -81,19 +84,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
         }
     }
     __syncthreads();
-    {
-        const double inv = 1.0 / s_norm;
-        float *lutf = reinterpret_cast<float *>(lut);
-        for (int e = threadIdx.x; e < 16 * p.n4; e += RN_THREADS) {
-            const int copy = e / (4 * p.n4), rem = e % (4 * p.n4);
-            const int a = (rem >> 2) * 4 + copy + (rem & 3);
-            const int k = abs(a - (p.radius + LUT_PAD));
-            lutf[e] = (k <= p.radius) ? (float)(exp(-0.5 / (p.sigma * p.sigma) * (double)k * (double)k) * inv) : 0.f;
-        }
-    }
+    fill_lut(lut, p.n4, p.radius, p.sigma, 1.0 / s_norm, threadIdx.x, RN_THREADS);
     __syncthreads();
-
-    const int lx = lane & 7, ly = lane >> 3;
 
     if (warp < NF) {
         // =============================== front warp ==========================================================
@@ -238,27 +230,12 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                     if (!flags[reg]) continue;
                     const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                     float acc[8][8];
-                    if (!accumulate_fast<false>(p, fs, n_live, rx0, ry0, lane, acc)) {
+                    bool mma;
+                    if (!accumulate_region<false>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma)) {
                         m = fmaxf(m, 0.f);
                         continue;
                     }
-                    const int x0 = rx0 + 4 * lx, y0 = ry0 + 8 * ly;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool yok = y0 + i < p.H;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (VEC) {
-                                const float m4 = fmaxf(fmaxf(acc[i][4 * h], acc[i][4 * h + 1]),
-                                                       fmaxf(acc[i][4 * h + 2], acc[i][4 * h + 3]));
-                                if (yok && x0 + 32 * h < p.W) m = fmaxf(m, m4);
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (yok && x0 + 32 * h + q < p.W) m = fmaxf(m, acc[i][4 * h + q]);
-                            }
-                        }
-                    }
+                    m = fmaxf(m, region_max<VEC>(p, rx0, ry0, lane, acc, mma));
                 }
                 vmax = warp_max(m);
                 scale = 1.f / vmax;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
@@ -302,7 +279,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 if (reg >= n_regions) break;
                 const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                 float acc[8][8];
-                const bool any = accumulate_fast<false>(p, fs, n_live, rx0, ry0, lane, acc);
+                bool mma;
+                const bool any = accumulate_region<false>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
                 float sc = any ? scale : 0.f;
                 if (n_pass == 2 && any && flags[reg]) {  // pin the maximum pixel to exactly 1 (see render.cu)
 #pragma unroll
@@ -311,7 +289,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                         for (int j = 0; j < 8; ++j) acc[i][j] = (acc[i][j] == vmax) ? 1.0f : acc[i][j] * sc;
                     sc = 1.0f;
                 }
-                store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc);
+                store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc, mma);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[slot]);
@@ -339,7 +317,7 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     // one front warp keeps up with the sparsest patterns; above 32 reflections per template two share the work
     int nf = p.cap <= 32 ? 1 : 2;
     if (const char *e = getenv("DS_RENDER_FRONTS")) nf = min(max(atoi(e), 1), 3);
-    const size_t smem = (size_t)4 * p.n4 * 16 + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
+    const size_t smem = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
     if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
     void (*const kerns[3][2])(RenderParams, int, int) = {{render_pipe_kernel<false, 1>, render_pipe_kernel<true, 1>},
