@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             s_norm = part;
             for (int s = 0; s < RP_SLOTS; ++s) {
                 mbar_init(&s_full[s], 1);
-                mbar_init(&s_empty[s], RP_RENDER_WARPS);
+                mbar_init(&s_empty[s], RP_RENDER_WARPS * 32);  // every lane arrives: its own reads of the slot are released
                 s_ticket[s] = 0;
             }
             for (int f = 0; f < NF; ++f) {
@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 }
                 store_region<VEC>(p, img, rx0, ry0, lane, acc, any, sc, mma);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[slot]);
+            mbar_arrive(&s_empty[slot]);
         }
     }
     // the last CTA to finish re-arms the ticket counters for the next launch

@@ -371,3 +371,24 @@ def test_render_fast_path_with_many_spots(eng, monkeypatch, pipe, cap, sigma, no
         assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
         if normalize and ref.max() > 0:   # (the lone spot of template 3 can fall outside the frame: all zeros)
             assert out[r].max() == 1.0
+
+
+def test_render_tensor_path_accuracy(eng, monkeypatch):
+    """The bf16 split-product tensor-core path against the float32 FMA path on the same dense templates: the
+    difference stays below 3e-5 of the peak (budget: 1e-4), and the normalised maximum is exactly 1 in both."""
+    import torch
+    rng = np.random.default_rng(11)
+    n, cap, shape = 4, 512, (256, 256)
+    X = np.zeros((n, cap, 3))
+    X[..., :2] = rng.uniform(-1.0, 1.0, (n, cap, 2))
+    I = rng.uniform(1, 5000, (n, cap))
+    cnt = torch.tensor([cap, 400, 300, 200], dtype=torch.int32, device=eng.device())
+    args = (cnt, torch.as_tensor(X, device=eng.device()), torch.as_tensor(I, device=eng.device()), shape, 10.0,
+            1 / 128, (127.5, 127.5))
+    out = {}
+    for mma in ("1", "0"):
+        monkeypatch.setenv("DS_RENDER_MMA", mma)
+        out[mma] = eng.render(*args).cpu().numpy()
+    assert not np.array_equal(out["1"], out["0"])            # the tensor-core path did run
+    assert np.abs(out["1"] - out["0"]).max() < 3e-5
+    assert all(o[r].max() == 1.0 for o in out.values() for r in range(n))

@@ -23,6 +23,28 @@ for name, rr in (("si", 1.0), ("large", 1.2)):          # resident table and str
                 engine.render(sp.count, sp.xyz, sp.intensity, shape, 6.0, rr / 64, (shape[1] // 2, shape[0] // 2), fast=fast)
     engine.render(sp.count, sp.xyz, sp.intensity, (24, 24), 10.0, rr / 12, (12, 12))     # kernel wider than the image
     engine.polar_flatten(sp.count, sp.xyz, sp.intensity, int(sp.count.max()), np.linspace(0, 1, 20), np.linspace(-3.2, 3.2, 30))
+# dense patterns: tensor-core regions (hit lists, reflect images, lane-pair exchange), both schedules, partial regions;
+# scan-line cull of K2; the bare rasteriser; mesh vertices through ds_beam_points
+rng = np.random.default_rng(3)
+for cap, shape in ((288, (256, 256)), (160, (100, 152)), (1024, (96, 200))):
+    n = 3
+    X = np.zeros((n, cap, 3))
+    X[..., :2] = rng.uniform(-1.05, 1.05, (n, cap, 2)) * (shape[1] / 256, shape[0] / 256)
+    I = rng.uniform(1, 500, (n, cap))
+    cnt = torch.tensor([cap, cap // 2, 17], dtype=torch.int32, device=engine.device())
+    for pipe in ("1", "0"):
+        os.environ["DS_RENDER_PIPE"] = pipe
+        engine.render(cnt, torch.as_tensor(X, device=engine.device()), torch.as_tensor(I, device=engine.device()),
+                      shape, 7.0, 1 / 128, ((shape[1] - 1) / 2, (shape[0] - 1) / 2))
+os.environ.pop("DS_RENDER_PIPE", None)
+os.environ["DS_SIM_LINES"] = "1"
+gt = gen._g_table(cases.phase("si"), 2.0, True, cases.DW)
+engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian")
+engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian_precession", precession_rad=0.0087)
+os.environ.pop("DS_SIM_LINES", None)
+from diffsims_b200.pattern.detector_functions import get_pattern_from_pixel_coordinates_and_intensities
+get_pattern_from_pixel_coordinates_and_intensities(rng.uniform(-8, 98, (40, 2)), rng.uniform(20, 900, 40), (70, 90), 2.5)
+beam_directions_device("cubic", 6.0, mesh="icosahedral")
 e, qd = beam_directions_device("hexagonal", 3.0)
 torch.cuda.synchronize()
 print("sanitize smoke ok", e.shape)
