@@ -386,7 +386,7 @@ def main():
             traffic = per_tmpl * B
         except Exception:
             traffic = None
-    roofline = dict(kernel="render_kernel (K3)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+    roofline = dict(kernel="render_pipe_kernel (K3, ds_render)", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=traffic, algorithmic_bytes_per_launch=algo_bytes,
                     kernel_ms=k3_ms, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     share_of_step=k3_ms * args.steps / elapsed_ms,
