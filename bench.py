@@ -360,6 +360,34 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- the literal drop-in call sequence of the reference, objects and all (context for e2e) ---------
+    if e2e is not None:
+        from diffsims_b200.crystal import Rotation
+        from diffsims_b200.generators.rotation_list_generators import get_beam_directions_grid
+        grid = get_beam_directions_grid("cubic", 0.5)        # BASELINE configs[1] as written: 4 186 directions
+        host_images = torch.empty((grid.shape[0], H, W), dtype=torch.float32).pin_memory()
+
+        def drop_in():
+            sim = gen.calculate_diffraction2d(si_phase(), Rotation.from_euler(grid, degrees=True),
+                                              reciprocal_radius=WORKLOAD["rr"], with_direct_beam=True,
+                                              max_excitation_error=WORKLOAD["s_max"])
+            dev_images = sim.get_diffraction_patterns((H, W), sigma=WORKLOAD["sigma"],
+                                                      calibration=WORKLOAD["calibration"])
+            host_images.copy_(dev_images)
+            return sim
+
+        drop_in()
+        torch.cuda.synchronize()
+        t_api = time.perf_counter()
+        for _ in range(3):
+            drop_in()
+        torch.cuda.synchronize()
+        t_api = (time.perf_counter() - t_api) / 3
+        e2e["drop_in_api"] = dict(
+            value=grid.shape[0] / t_api, unit=UNIT, templates=int(grid.shape[0]), seconds=t_api,
+            call="get_beam_directions_grid('cubic', 0.5) -> SimulationGenerator.calculate_diffraction2d -> "
+                 "Simulation2D.get_diffraction_patterns -> host float32 (Python objects included, wall clock)")
+
     # context for the roofline: the pure-write ceiling of this GPU (the driver's peak is a read+write copy)
     fill_ms = []
     for _ in range(4):
