@@ -434,18 +434,20 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         while (ts < 2 * cap) ts <<= 1;
         p.table_size = ts;
         p.n4 = lut_entries(radius);
-        // per-warp hit lists of the tensor-core path for dense regions (DS_RENDER_MMA=0 switches it off)
+        // Tensor-core path for dense regions (DS_RENDER_MMA=0 switches it off).  A region is reached by about `frac`
+        // of a template's spots; templates expected to put fewer than mma_min spots into a region skip the hit
+        // lists, and launches whose capacity says that hardly any template is that dense do not carry them at all
+        // (measured: Si r = 2, cap 96, 18 spots on average loses 2 % to them).
         p.hits_bytes = 0;
-        if (!wide && cap >= MMA_MIN_HITS && cap <= 4096 && !(getenv("DS_RENDER_MMA") && atoi(getenv("DS_RENDER_MMA")) == 0))
-            p.hits_bytes = RN_WARPS * ((2 * cap * 2 + 15) & ~15);  // 2 cap entries: spots + their reflect images
         p.mma_min = MMA_MIN_HITS;
         if (const char *e = getenv("DS_RENDER_MMA_MIN")) p.mma_min = atoi(e) > 1 ? atoi(e) : MMA_MIN_HITS;
-        {   // a region is reached by about this fraction of a template's spots; templates expected to put fewer
-            // than mma_min spots into a region skip the hit lists altogether
-            const double frac = fmin(1.0, (2.0 * radius + 1 + RN_RW) * (2.0 * radius + 1 + RN_RH) / ((double)W * H));
-            p.mma_tmpl_min = (int)ceil(p.mma_min / frac);
-            if (const char *e = getenv("DS_RENDER_MMA_TMPL_MIN")) p.mma_tmpl_min = atoi(e);
-        }
+        const double frac = fmin(1.0, (2.0 * radius + 1 + RN_RW) * (2.0 * radius + 1 + RN_RH) / ((double)W * H));
+        p.mma_tmpl_min = (int)ceil(p.mma_min / frac);
+        if (const char *e = getenv("DS_RENDER_MMA_TMPL_MIN")) p.mma_tmpl_min = atoi(e);
+        const char *force = getenv("DS_RENDER_MMA");
+        const bool want = force ? atoi(force) != 0 : cap >= 2 * p.mma_tmpl_min;
+        if (want && !wide && cap >= p.mma_min && cap <= 4096)
+            p.hits_bytes = RN_WARPS * ((2 * cap * 2 + 15) & ~15);  // 2 cap entries: spots + their reflect images
         lut_bytes = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes;
         group_bytes = (int)((size_t)ts * 8 + (size_t)cap * 16);
     } else {

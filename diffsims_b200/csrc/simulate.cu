@@ -389,39 +389,39 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                 }
             }
         } else {
-        if (n_tiles > 1) issue(0, 0);
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = (n_tiles > 1) ? (t & 1) : 0;
-            if (n_tiles > 1) {
-                if (t + 1 < n_tiles) issue(t + 1, (t + 1) & 1);
-                mbar_wait(&s_bar[buf], phase[buf]);
-                phase[buf] ^= 1;
-            }
-            const int n = min(tile_g, p.n_g - t * tile_g);
-            const uint32_t tile_s = tile_base_s + (buf ? (uint32_t)tile_g * 16u : 0u);
-            if (active) {
-                for (int i0 = 0; i0 < n; i0 += 128) {
-                    // four independent g per lane: loads and tests overlap, ballots are consumed in table order
-                    bool cands[4];
-                    float4 gk[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        gk[k] = lds_f4(tile_s + 16u * (uint32_t)min(i0 + 32 * k + lane, n - 1));
-                    bool any = false;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float4 g = gk[k];
-                        const float z = fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z));
-                        cands[k] = coarse_test(z, g.w, thr, two_rs, prec_on, P_z, P_t) && (i0 + 32 * k + lane < n);
-                        any |= cands[k];
-                    }
-                    if (!__any_sync(0xffffffffu, any)) continue;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) append(cands[k], t * tile_g + i0 + 32 * k + lane);
+            if (n_tiles > 1) issue(0, 0);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int buf = (n_tiles > 1) ? (t & 1) : 0;
+                if (n_tiles > 1) {
+                    if (t + 1 < n_tiles) issue(t + 1, (t + 1) & 1);
+                    mbar_wait(&s_bar[buf], phase[buf]);
+                    phase[buf] ^= 1;
                 }
+                const int n = min(tile_g, p.n_g - t * tile_g);
+                const uint32_t tile_s = tile_base_s + (buf ? (uint32_t)tile_g * 16u : 0u);
+                if (active) {
+                    for (int i0 = 0; i0 < n; i0 += 128) {
+                        // four independent g per lane: loads and tests overlap, ballots are consumed in table order
+                        bool cands[4];
+                        float4 gk[4];
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            gk[k] = lds_f4(tile_s + 16u * (uint32_t)min(i0 + 32 * k + lane, n - 1));
+                        bool any = false;
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 g = gk[k];
+                            const float z = fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z));
+                            cands[k] = coarse_test(z, g.w, thr, two_rs, prec_on, P_z, P_t) && (i0 + 32 * k + lane < n);
+                            any |= cands[k];
+                        }
+                        if (!__any_sync(0xffffffffu, any)) continue;
+    #pragma unroll
+                        for (int k = 0; k < 4; ++k) append(cands[k], t * tile_g + i0 + 32 * k + lane);
+                    }
+                }
+                if (n_tiles > 1) __syncthreads();  // everyone is done with `buf` before it is refilled
             }
-            if (n_tiles > 1) __syncthreads();  // everyone is done with `buf` before it is refilled
-        }
         }
         if (active) {
             if (n_list > 0) refine<MODEL>(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
