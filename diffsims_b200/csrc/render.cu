@@ -39,7 +39,7 @@ __device__ __forceinline__ void group_sync(int group) {
     }
 }
 
-template <bool FAST, int G, bool WIDE, bool VEC>
+template <bool FAST, int G, bool WIDE, bool VEC, bool DENSE>
 __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParams p, const int group_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NGROUPS = RN_WARPS / G;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                 float acc[8][8];
                 bool any, mma = false;
                 if (FAST)
-                    any = accumulate_region<WIDE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
+                    any = accumulate_region<WIDE, DENSE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
                 else
                     any = accumulate_slow(p, ss, n_live, rx0, ry0, lane, acc);
                 if (!store) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
     }
 }
 
-template <bool FAST, int G, bool WIDE, bool VEC>
+template <bool FAST, int G, bool WIDE, bool VEC, bool DENSE = false>
 static int launch_render(const RenderParams &p, int group_bytes, size_t lut_bytes, cudaStream_t st) {
     constexpr int NGROUPS = RN_WARPS / G;
     const size_t smem = lut_bytes + (size_t)NGROUPS * group_bytes;
@@ -368,15 +368,15 @@ static int launch_render(const RenderParams &p, int group_bytes, size_t lut_byte
                smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(render_kernel<FAST, G, WIDE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(render_kernel<FAST, G, WIDE, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FAST, G, WIDE, VEC>, RN_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FAST, G, WIDE, VEC, DENSE>, RN_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     const int want = (p.n_tmpl + NGROUPS - 1) / NGROUPS;
     const int grid = want < num_sms() * per_sm ? want : num_sms() * per_sm;
-    render_kernel<FAST, G, WIDE, VEC><<<grid, RN_THREADS, smem, st>>>(p, group_bytes);
+    render_kernel<FAST, G, WIDE, VEC, DENSE><<<grid, RN_THREADS, smem, st>>>(p, group_bytes);
     return check_launch("ds_render");
 }
 
@@ -481,6 +481,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     if (!fast && G != 1) G = 8;  // the sub-pixel path is instantiated for G = 1 and G = 8 only
     group_bytes = bytes_for(G);
 #define DS_RN(F, GG, WD, V) launch_render<F, GG, WD, V>(p, group_bytes, lut_bytes, st)
+#define DS_RND(F, GG, WD, V) launch_render<F, GG, WD, V, true>(p, group_bytes, lut_bytes, st)
+    // the tensor-core path exists in the aligned, non-wide fast instantiations with G >= 2
+    const bool dense = p.hits_bytes > 0;
     // rows that are not 16-byte aligned (W % 4 != 0) and kernels wider than the image take the
     // general-purpose instantiations; the common case gets the lean ones
     if ((W & 3) != 0) return fast ? (wide ? DS_RN(true, 8, true, false) : DS_RN(true, 8, false, false))
@@ -489,9 +492,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     if (fast) {
         switch (G) {
             case 1: return DS_RN(true, 1, false, true);
-            case 2: return DS_RN(true, 2, false, true);
-            case 4: return DS_RN(true, 4, false, true);
-            default: return DS_RN(true, 8, false, true);
+            case 2: return dense ? DS_RND(true, 2, false, true) : DS_RN(true, 2, false, true);
+            case 4: return dense ? DS_RND(true, 4, false, true) : DS_RN(true, 4, false, true);
+            default: return dense ? DS_RND(true, 8, false, true) : DS_RN(true, 8, false, true);
         }
     } else {
         switch (G) {
@@ -500,4 +503,5 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         }
     }
 #undef DS_RN
+#undef DS_RND
 }

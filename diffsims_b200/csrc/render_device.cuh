@@ -310,10 +310,11 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // the direct delta at c and its mirror images at -c - 1 (image 1, spots within R of the low border) and
 // 2n - 1 - c (image 2, high border); an image is listed only for regions it reaches, as one more rank-1 term,
 // so every tap of the matrix operands is a single table read.
-template <bool WIDE>
+template <bool WIDE, bool DENSE>
 __device__ __forceinline__ bool accumulate_region(const RenderParams &p, const FastSmem &s, int n_live, int rx0,
                                                   int ry0, int lane, float (&acc)[8][8], uint32_t hits_s, bool &mma) {
     mma = false;
+    if (!DENSE) return accumulate_fast<WIDE>(p, s, n_live, rx0, ry0, lane, acc);  // kernels compiled without the path
     // (the template-level threshold keeps the list building away from patterns too sparse to fill a chunk)
     if (WIDE || hits_s == 0u || n_live < p.mma_tmpl_min) return accumulate_fast<WIDE>(p, s, n_live, rx0, ry0, lane, acc);
     const int R = p.radius;

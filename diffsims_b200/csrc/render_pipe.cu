@@ -24,7 +24,7 @@ struct PipeHeader {  // 32 bytes at the start of a slot
     float scale, vmax, pad1, pad2;
 };
 
-template <bool VEC, int NF>
+template <bool VEC, int NF, bool DENSE>
 __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const RenderParams p, const int slot_bytes,
                                                                     const int front_bytes) {
     constexpr int RP_SLOTS = 2 * NF;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                     const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                     float acc[8][8];
                     bool mma;
-                    if (!accumulate_region<false>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma)) {
+                    if (!accumulate_region<false, DENSE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma)) {
                         m = fmaxf(m, 0.f);
                         continue;
                     }
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 const int rx0 = (reg % nrx) * RN_RW, ry0 = (reg / nrx) * RN_RH;
                 float acc[8][8];
                 bool mma;
-                const bool any = accumulate_region<false>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
+                const bool any = accumulate_region<false, DENSE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
                 float sc = any ? scale : 0.f;
                 if (n_pass == 2 && any && flags[reg]) {  // pin the maximum pixel to exactly 1 (see render.cu)
 #pragma unroll
@@ -319,12 +319,18 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     const size_t smem = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
     if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
-    void (*const kerns[3][2])(RenderParams, int, int) = {{render_pipe_kernel<false, 1>, render_pipe_kernel<true, 1>},
-                                                         {render_pipe_kernel<false, 2>, render_pipe_kernel<true, 2>},
-                                                         {render_pipe_kernel<false, 3>, render_pipe_kernel<true, 3>}};
-    void (*kern)(RenderParams, int, int) = kerns[nf - 1][vec ? 1 : 0];
-    static bool attr[6] = {false, false, false, false, false, false};
-    const int slot_id = (nf - 1) * 2 + (vec ? 1 : 0);
+    // DENSE: the instantiation that carries the tensor-core path (larger code; only when hit lists were set up)
+    void (*const kerns[2][3][2])(RenderParams, int, int) = {
+        {{render_pipe_kernel<false, 1, false>, render_pipe_kernel<true, 1, false>},
+         {render_pipe_kernel<false, 2, false>, render_pipe_kernel<true, 2, false>},
+         {render_pipe_kernel<false, 3, false>, render_pipe_kernel<true, 3, false>}},
+        {{render_pipe_kernel<false, 1, true>, render_pipe_kernel<true, 1, true>},
+         {render_pipe_kernel<false, 2, true>, render_pipe_kernel<true, 2, true>},
+         {render_pipe_kernel<false, 3, true>, render_pipe_kernel<true, 3, true>}}};
+    const int dense = p.hits_bytes > 0 ? 1 : 0;
+    void (*kern)(RenderParams, int, int) = kerns[dense][nf - 1][vec ? 1 : 0];
+    static bool attr[12] = {false};
+    const int slot_id = dense * 6 + (nf - 1) * 2 + (vec ? 1 : 0);
     if (smem > 48 * 1024 && !attr[slot_id]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr[slot_id] = true;
