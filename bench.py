@@ -139,7 +139,7 @@ def run_reference_arm(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons every 20 ms; the summary uses the samples taken inside the timed
+    """SM clocks / throttle reasons sampled while the steps run (NVML every 5 ms, else nvidia-smi every 20 ms); the summary uses the samples taken inside the timed
     region (``mark_start`` .. ``mark_end``) and falls back to the whole window when the region is shorter
     than a sampling period."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -151,6 +151,8 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self._run_nvml():
+            return
         try:
             proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                      "--format=csv,noheader,nounits", "-lms", "20"],
@@ -164,6 +166,31 @@ class ClockSampler:
                     break
         finally:
             proc.kill()
+
+    def _run_nvml(self):
+        """The same fields through NVML in this thread (5 ms period; an nvidia-smi process answers too slowly on
+        an 8-GPU box to land inside a 0.1 s timed region).  False if NVML is unavailable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_of = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                                 getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = (0x8, 0x40, 0x20, 0x4)   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = int(reasons_of(h)) if reasons_of else 0
+                self.samples.append((time.perf_counter(), [str(sm), str(mx)] +
+                                     ["Active" if mask & b else "Not Active" for b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+        return True
 
     def __enter__(self):
         self.thread.start()
