@@ -348,6 +348,7 @@ def main():
     elapsed_ms = t0.elapsed_time(t1)
     launches = 4 * args.steps if graph is not None else builder.launches
     k3_ms = float(np.mean([a.elapsed_time(b) for a, b in k3_events]))
+    builder.assert_no_overflow(spots)           # the unchecked timed passes stayed inside the calibrated capacity
     all_counts = gather_counts(spots.count)     # the single collective of a sharded build (not timed)
     mean_spots = float(all_counts.float().mean().item())
 
@@ -375,6 +376,7 @@ def main():
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        builder.check_capacity()
         # correctness guard: the host images are the device images
         assert torch.equal(out_pin[:64], images[:64].cpu()), "e2e images differ from the device-resident images"
         e2e = dict(value=world * B * n_e2e / (float(te.item()) * 1e-3), unit=UNIT,

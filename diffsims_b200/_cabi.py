@@ -39,7 +39,7 @@ def lib():
         raise NativeLibraryError(f"ABI version {L.ds_abi_version()} != {ABI_VERSION}: rebuild the library")
     P, I, D = c_void_p, c_int32, c_double
     L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P]
-    L.ds_pack_gtable.argtypes = [P, I, P, P]
+    L.ds_pack_gtable.argtypes = [P, I, P, P, P, I, D]
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]

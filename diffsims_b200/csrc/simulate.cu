@@ -112,6 +112,12 @@ __device__ __forceinline__ bool coarse_test(float z, float g2, float thr, float 
     return (r2 + two_rpt + v * (v - 2.0f * P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * P_z) <= 0.0f);
 }
 
+// scan-line mode rebuilds g from the line tables; rows marked extinct by ds_pack_gtable (|g|^2 = +inf in the packed
+// table) are dropped among the few rows that pass the coarse test
+__device__ __forceinline__ bool live_row(const SimParams &p, int index) {
+    return __ldg(reinterpret_cast<const float *>(p.g_f32) + 4 * (size_t)index + 3) < INFINITY;
+}
+
 struct WarpState {
     // float64 active rotation matrix, row-major
     double m[9];
@@ -331,7 +337,8 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                             const float gx = fmaf(fi, p.step[0], g0.x), gy = fmaf(fi, p.step[1], g0.y),
                                         gz = fmaf(fi, p.step[2], g0.z);
                             const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
-                            if (coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t))
+                            if (coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t) &&
+                                live_row(p, start + ilo + r))
                                 bits |= 1u << r;
                         }
                         const int mine = __popc(bits);
@@ -381,7 +388,8 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                                 const float gx = fmaf(fi, p.step[0], hx), gy = fmaf(fi, p.step[1], hy),
                                             gz = fmaf(fi, p.step[2], hz);
                                 const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
-                                cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t);
+                                cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t) &&
+                                       live_row(p, first + r);
                             }
                             append(cand, first + r);
                         }
@@ -473,11 +481,17 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
     if (lane == 0 && local_max_count > 0) atomicMax(p.max_count, local_max_count);
 }
 
-__global__ void pack_gtable_kernel(int n_g, const double *__restrict__ g, float4 *__restrict__ out) {
+// Rows whose |F|^2 can never pass the minimum-intensity cut (extinct reflections of centred / glide lattices,
+// I0 <= rel_cut * I0[ref_row]) get |g|^2 = +inf: the coarse test then rejects them for free (see ds_pack_gtable
+// in the header for why this leaves every result unchanged).
+__global__ void pack_gtable_kernel(int n_g, const double *__restrict__ g, float4 *__restrict__ out,
+                                   const double *__restrict__ I0, int ref_row, double rel_cut) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_g) {
         const double x = g[3 * i], y = g[3 * i + 1], z = g[3 * i + 2];
-        out[i] = make_float4((float)x, (float)y, (float)z, (float)(x * x + y * y + z * z));
+        float g2 = (float)(x * x + y * y + z * z);
+        if (I0 != nullptr && I0[i] <= rel_cut * I0[ref_row]) g2 = INFINITY;
+        out[i] = make_float4((float)x, (float)y, (float)z, g2);
     }
 }
 
@@ -494,12 +508,15 @@ int num_sms() {
 
 }  // namespace ds
 
-extern "C" int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz, float *g_f32) {
+extern "C" int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz, float *g_f32, const double *g_I0,
+                              int32_t ref_row, double rel_cut) {
     using namespace ds;
     DS_REQUIRE(n_g >= 0, "ds_pack_gtable: negative size");
     if (n_g == 0) return 0;
+    const bool mark = g_I0 != nullptr && ref_row >= 0 && rel_cut > 0.0;
+    DS_REQUIRE(!mark || (ref_row < n_g && rel_cut < 1.0), "ds_pack_gtable: bad reference row / relative cut");
     pack_gtable_kernel<<<(n_g + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        n_g, g_xyz, reinterpret_cast<float4 *>(g_f32));
+        n_g, g_xyz, reinterpret_cast<float4 *>(g_f32), mark ? g_I0 : nullptr, ref_row, rel_cut);
     return check_launch("ds_pack_gtable");
 }
 

@@ -12,6 +12,8 @@ import warnings
 from dataclasses import dataclass
 from pathlib import Path
 
+import os
+
 import numpy as np
 import torch
 
@@ -153,6 +155,7 @@ class GTable:
     line_start: torch.Tensor | None = None  # [n_lines + 1 (padded)] int32 device
     line_step: np.ndarray | None = None     # [3] float64 host
     n_lines: int = 0
+    marked: bool = False                    # extinct rows carry |g|^2 = +inf in f32 (ds_pack_gtable)
 
     @property
     def n(self):
@@ -210,16 +213,21 @@ class GTablePlan:
             self.lines = (torch.as_tensor(g0, device=dev), torch.as_tensor(starts_p, device=dev),
                           np.ascontiguousarray(step, dtype=np.float64), len(starts) - 1)
 
-    def run(self):
+    def run(self, extinct_rel_cut=0.0):
+        """``extinct_rel_cut`` > 0 (and a table that ends with the direct beam): rows whose |F|^2 is below that
+        fraction of |F(000)|^2 are marked extinct for the cull of K2 (see ds_pack_gtable in the header)."""
         n = self.xyz_d.shape[0]
         dev = self.xyz_d.device
         I0 = torch.empty((n,), dtype=torch.float64, device=dev)
         f32 = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        mark = bool(n) and extinct_rel_cut > 0.0 and not np.any(self.hkl[-1])   # last row = (000)
         if n:
             launch_structure_factors(self.atoms, self.hkl_d, self.gnorm_d, None, None, I0)
-            _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), n, _cabi.ptr(self.xyz_d), _cabi.ptr(f32)),
-                        "ds_pack_gtable")
-        gt = GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max)
+            _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), n, _cabi.ptr(self.xyz_d), _cabi.ptr(f32),
+                                                   _cabi.ptr(I0) if mark else None, n - 1 if mark else -1,
+                                                   float(extinct_rel_cut) if mark else 0.0), "ds_pack_gtable")
+        gt = GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max,
+                    marked=bool(mark))
         if self.lines is not None:
             gt.line_g0, gt.line_start, gt.line_step, gt.n_lines = self.lines
         return gt
@@ -241,6 +249,9 @@ class SpotTable:
     intensity: torch.Tensor  # [n_rot, cap] float64
     exc: torch.Tensor | None
     cap: int
+    # [1] int32 device word: the largest number of reflections any rotation produced BEFORE the minimum-intensity
+    # cut; rows are only complete when it is <= cap (checked by simulate(check_overflow=True), else by the caller)
+    max_count: torch.Tensor | None = None
 
     @property
     def n_rot(self):
@@ -277,19 +288,22 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
         if gt.n == 0 or n_rot == 0:
             count.zero_()
             return SpotTable(count, g_index, xyz, inten, exc, cap)
+        # measured (tools/bench_configs.py): once the extinct rows are marked, the plain cull over the packed table
+        # beats the scan-line cull, which rebuilds every row of a line (DS_SIM_LINES=1 still forces it)
+        n_lines = gt.n_lines if (not gt.marked or os.environ.get("DS_SIM_LINES") == "1") else 0
         rc = _cabi.lib().ds_simulate(
             _stream(), n_rot, _cabi.ptr(q), gt.n, _cabi.ptr(gt.xyz), _cabi.ptr(gt.f32), _cabi.ptr(gt.I0),
             float(gt.g_max), 1.0 / float(wavelength), float(s_max), float(width), model_id,
             float(minima_number), float(precession_rad), float(min_intensity), cap,
             _cabi.ptr(count), _cabi.ptr(g_index), _cabi.ptr(xyz), _cabi.ptr(inten), _cabi.ptr(exc),
-            _cabi.ptr(max_count), int(gt.n_lines), _cabi.ptr(gt.line_g0), _cabi.ptr(gt.line_start),
+            _cabi.ptr(max_count), int(n_lines), _cabi.ptr(gt.line_g0), _cabi.ptr(gt.line_start),
             None if gt.line_step is None else gt.line_step.ctypes.data_as(_cabi.c_void_p))
         _cabi.check(rc, "ds_simulate")
         if not check_overflow:
-            return SpotTable(count, g_index, xyz, inten, exc, cap)
+            return SpotTable(count, g_index, xyz, inten, exc, cap, max_count)
         need = int(max_count.item())
         if need <= cap:
-            return SpotTable(count, g_index, xyz, inten, exc, cap)
+            return SpotTable(count, g_index, xyz, inten, exc, cap, max_count)
         cap = (need + 31) // 32 * 32
 
 

@@ -99,9 +99,20 @@ class SimulationGenerator:
         xyz = hkl.astype(float) @ np.asarray(lat.recbase, dtype=float).T
         return engine.GTablePlan(phase.structure, hkl, xyz, debye_waller_factors, self.scattering_params)
 
+    def _extinct_rel_cut(self, with_direct_beam):
+        """Relative |F|^2 below which a reflection can never pass ``minimum_intensity`` (0 = do not mark): needs
+        the direct beam in the set (it is always excited, so max(I) >= sf(0) |F(000)|^2) and a shape factor
+        bounded by its value at s = 0 -- see ds_pack_gtable in include/diffsims_b200.h."""
+        model, _ = self._native_model()
+        if (with_direct_beam and self.precession_angle == 0 and self.minimum_intensity > 0
+                and model in ("binary", "linear", "atanc", "lorentzian")):
+            return min(0.5 * self.minimum_intensity, 0.5)
+        return 0.0
+
     def _g_table(self, phase, reciprocal_radius, with_direct_beam, debye_waller_factors):
         """Per-phase g table with structure factors (K1)."""
-        return self._g_plan(phase, reciprocal_radius, with_direct_beam, debye_waller_factors).run()
+        plan = self._g_plan(phase, reciprocal_radius, with_direct_beam, debye_waller_factors)
+        return plan.run(self._extinct_rel_cut(with_direct_beam))
 
     def _simulate_phase(self, phase, rotation, reciprocal_radius, with_direct_beam, max_excitation_error,
                         shape_factor_width, debye_waller_factors):
@@ -206,7 +217,8 @@ class SimulationGenerator:
         xyz_d = torch.as_tensor(np.ascontiguousarray(xyz), device=dev)
         f32 = torch.empty((xyz.shape[0], 4), dtype=torch.float32, device=dev)
         engine._cabi.check(engine._cabi.lib().ds_pack_gtable(
-            engine._stream(), xyz.shape[0], engine._cabi.ptr(xyz_d), engine._cabi.ptr(f32)), "ds_pack_gtable")
+            engine._stream(), xyz.shape[0], engine._cabi.ptr(xyz_d), engine._cabi.ptr(f32), None, -1, 0.0),
+            "ds_pack_gtable")
         gt = engine.GTable(hkl=hkl, xyz_host=xyz, xyz=xyz_d, f32=f32,
                            I0=torch.ones(xyz.shape[0], dtype=torch.float64, device=dev),
                            g_max=float(np.sqrt((xyz ** 2).sum(axis=1)).max()) if xyz.size else 0.0)

@@ -73,7 +73,7 @@ class TemplateLibraryBuilder:
         The integer hkl enumeration and the atom table are a host-side plan built on first use."""
         if self.plan is None:
             self.plan = self.gen._g_plan(self.phase, self.rr, self.with_direct_beam, self.dw)
-        self.gtable = self.plan.run()
+        self.gtable = self.plan.run(self.gen._extinct_rel_cut(self.with_direct_beam))
         self.launches += 2  # structure factors + table packing
         if self.cap is None:
             self.cap = engine.estimate_cap(self.gtable.n, self.gtable.g_max, self.s_max, self.prec)
@@ -96,9 +96,17 @@ class TemplateLibraryBuilder:
     def calibrate_cap(self, quats_dev):
         """One untimed overflow-checked pass that fixes ``cap`` for the rotation list."""
         spots = self.simulate(quats_dev, check_overflow=True)
-        need = int(spots.count.max().item()) if spots.n_rot else 0
+        # the rows must hold every reflection that passes the excitation-error cut, i.e. the count BEFORE the
+        # minimum-intensity cut (K2 compacts in place); the later unchecked passes rely on this capacity
+        need = int(spots.max_count.item()) if spots.n_rot and spots.max_count is not None else 0
         self.cap = max(32, (max(need, 1) + 31) // 32 * 32)
         return self.cap
+
+    def assert_no_overflow(self, spots):
+        """Host check (synchronises) that an unchecked pass did not outgrow the calibrated capacity."""
+        if spots.max_count is not None and int(spots.max_count.item()) > spots.cap:
+            raise RuntimeError(f"{int(spots.max_count.item())} reflections in one rotation exceed the capacity "
+                               f"{spots.cap}: call calibrate_cap() on this rotation list")
 
     def run_device(self, quats_dev, out_images):
         """Device-resident pass: K1 + K2 + K3 on the current stream; returns the SpotTable."""
@@ -137,6 +145,7 @@ class TemplateLibraryBuilder:
         ready = torch.cuda.Event()
         ready.record(main)
         h2d = d2h = 0
+        worst = torch.zeros(2, dtype=torch.int32, device=dev)   # per stream: largest pre-cut reflection count
         for i, lo in enumerate(range(0, n, chunk)):
             hi = min(lo + chunk, n)
             st, buf = streams[i & 1], bufs[i & 1][: hi - lo]
@@ -145,6 +154,8 @@ class TemplateLibraryBuilder:
                 q = quats_host[lo:hi].to(dev, non_blocking=True)
                 spots = self.simulate(q)
                 self.render(spots, buf)
+                w = worst[(i & 1):(i & 1) + 1]
+                torch.maximum(w, spots.max_count, out=w)
                 out_host[lo:hi].copy_(buf, non_blocking=True)
                 if counts_host is not None:
                     counts_host[lo:hi].copy_(spots.count, non_blocking=True)
@@ -153,7 +164,15 @@ class TemplateLibraryBuilder:
             d2h += (hi - lo) * H * W * 4
         for st in streams:
             main.wait_stream(st)
+        self.last_max_count = worst   # device word; compare with self.cap after synchronising (check_capacity)
         return h2d, d2h
+
+    def check_capacity(self):
+        """After ``run_host`` (synchronises): raise if a chunk produced more reflections than the rows hold."""
+        worst = int(self.last_max_count.max().item())
+        if worst > self.cap:
+            raise RuntimeError(f"{worst} reflections in one rotation exceed the capacity {self.cap}: "
+                               f"call calibrate_cap() on this rotation list")
 
 
 def gather_counts(local_counts):

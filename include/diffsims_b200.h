@@ -72,8 +72,17 @@ int ds_structure_factors(void *stream,
 /*
  * Pack the per-phase g table for K2: out[g] = (gx, gy, gz, |g|^2) as float (16-byte rows,
  * the tile format K2 stages into shared memory with cp.async.bulk).
+ *
+ * Optional extinction marking (g_I0 = NULL, ref_row < 0 or rel_cut <= 0: none): rows with
+ * g_I0[g] <= rel_cut * g_I0[ref_row] get |g|^2 = +inf, which the float32 cull of ds_simulate rejects, so the
+ * systematically absent reflections of centred lattices (3/4 of an F lattice, 13/16 of diamond) cost no float64
+ * work.  This is exact when (i) ref_row is the direct beam (000), which every rotation excites with s = 0,
+ * (ii) the shape factor obeys sf(s) <= sf(0) (binary, linear, atanc, lorentzian without precession) and
+ * (iii) rel_cut <= min_intensity / 2: such a row has I = sf(s) I0 <= rel_cut sf(0) I0[000] < max(I) min_intensity
+ * and the reference's cut I > max(I) * minimum_intensity (simulation_generator.py:237-241) removes it anyway.
  */
-int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz /*[n_g][3]*/, float *g_f32 /*[n_g][4]*/);
+int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz /*[n_g][3]*/, float *g_f32 /*[n_g][4]*/,
+                   const double *g_I0 /*[n_g] or NULL*/, int32_t ref_row, double rel_cut);
 
 /*
  * K2 -- fused rotate / excitation error / shape factor / cull / threshold over

@@ -590,3 +590,35 @@ class TestGetPatternFromPixelCoordinatesAndIntensities:
         for coords, key in ((xy, "outside_float"), (xy_int, "outside_int")):
             got = self.f(coords, inten, (70, 90), 2.5)
             assert np.abs(got - gold[key]).max() <= 1e-4 * gold[key].max()
+
+
+def test_library_builder_capacity_covers_the_pre_cut_count():
+    """K2 writes every reflection that passes the excitation-error cut and compacts after the minimum-intensity cut,
+    so the calibrated capacity must cover the count BEFORE that cut (with the extinction marking off, Si has five
+    forbidden reflections per allowed one); unchecked passes expose the device-side maximum for a later check."""
+    import torch
+    from diffsims_b200.library import TemplateLibraryBuilder, active_quaternions
+    from tests.helpers import random_quats
+    gen = ds.SimulationGenerator(200, shape_factor_model="sinc")     # sinc: no extinction marking
+    assert gen._extinct_rel_cut(True) == 0.0
+    b = TemplateLibraryBuilder(gen, cases.phase("si"), reciprocal_radius=2.0, max_excitation_error=0.05,
+                               shape=(64, 64), sigma=2, calibration=2 / 32)
+    b.prepare()
+    q = np.vstack([[1.0, 0, 0, 0], random_quats(63, 2)])
+    qd = torch.as_tensor(active_quaternions(q), device=engine_device())
+    cap = b.calibrate_cap(qd)
+    sp = b.simulate(qd)
+    assert int(sp.max_count.item()) <= cap and int(sp.count.max().item()) < int(sp.max_count.item())
+    b.assert_no_overflow(sp)
+    ref = gen.calculate_diffraction2d(cases.phase("si"), Rotation(q), reciprocal_radius=2.0, max_excitation_error=0.05)
+    for r in (0, 1, 17):
+        assert int(sp.count[r]) == ref.coordinates[r].size
+    b.cap = 32                                   # too small on purpose: the check must notice
+    sp = b.simulate(qd)
+    with pytest.raises(RuntimeError):
+        b.assert_no_overflow(sp)
+
+
+def engine_device():
+    from diffsims_b200 import engine
+    return engine.device()

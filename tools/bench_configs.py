@@ -48,6 +48,7 @@ for name, ph, kv, rr, s_max, model, sigma, scale in CONFIGS:
     q = torch.as_tensor(active_quaternions(random_quats(n, 0)), device=dev)
     b.calibrate_cap(q)
     sp = b.simulate(q)
+    b.assert_no_overflow(sp)
     t2 = timeit(lambda: b.simulate(q))
     img = torch.empty((n, 256, 256), dtype=torch.float32, device=dev)
     t3 = timeit(lambda: b.render(sp, img))
