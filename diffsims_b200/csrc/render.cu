@@ -436,8 +436,10 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         p.n4 = lut_entries(radius);
         // Tensor-core path for dense regions (DS_RENDER_MMA=0 switches it off).  A region is reached by about `frac`
         // of a template's spots; templates expected to put fewer than mma_min spots into a region skip the hit
-        // lists, and launches whose capacity says that hardly any template is that dense do not carry them at all
-        // (measured: Si r = 2, cap 96, 18 spots on average loses 2 % to them).
+        // lists, and launches whose capacity says that few templates are that dense do not carry them at all: the
+        // path pays from roughly 100 spots per template on (measured at sigma = 10, 256 x 256: capacity 288 /
+        // 177 spots on average 1.75 x faster, capacity 864 / 680 spots 3.7 x; capacity 96 / 39 spots 1.1 - 2 x SLOWER
+        // because of the list building in front of mostly sparse regions).
         p.hits_bytes = 0;
         p.mma_min = MMA_MIN_HITS;
         if (const char *e = getenv("DS_RENDER_MMA_MIN")) p.mma_min = atoi(e) > 1 ? atoi(e) : MMA_MIN_HITS;
@@ -445,7 +447,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         p.mma_tmpl_min = (int)ceil(p.mma_min / frac);
         if (const char *e = getenv("DS_RENDER_MMA_TMPL_MIN")) p.mma_tmpl_min = atoi(e);
         const char *force = getenv("DS_RENDER_MMA");
-        const bool want = force ? atoi(force) != 0 : cap >= 2 * p.mma_tmpl_min;
+        const bool want = force ? atoi(force) != 0 : cap >= 3 * p.mma_tmpl_min;
         if (want && !wide && cap >= p.mma_min && cap <= 4096)
             p.hits_bytes = RN_WARPS * ((2 * cap * 2 + 15) & ~15);  // 2 cap entries: spots + their reflect images
         lut_bytes = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes;
