@@ -458,7 +458,8 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64+f32", data="synthetic",
-                config=dict(workload=WORKLOAD["workload"], templates_per_gpu_per_step=B, n_g=int(builder.gtable.n),
+                config=dict(workload=WORKLOAD["workload"], templates_per_gpu_per_step=B, n_g=int(builder.plan.hkl.shape[0]),
+                            n_g_not_extinct=int(builder.gtable.n),
                             mean_spots_per_template=mean_spots, spot_capacity=int(builder.cap),
                             l2="each step writes %.1f GB of templates per GPU (>> 126 MB L2), so no input or "
                                "output survives in L2 between steps" % (algo_bytes / 1e9),

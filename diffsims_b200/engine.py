@@ -156,6 +156,7 @@ class GTable:
     line_step: np.ndarray | None = None     # [3] float64 host
     n_lines: int = 0
     marked: bool = False                    # extinct rows carry |g|^2 = +inf in f32 (ds_pack_gtable)
+    rows: np.ndarray | None = None          # rows of the enumerated g set this table keeps (None = all of them)
 
     @property
     def n(self):
@@ -194,11 +195,16 @@ class GTablePlan:
 
     def __init__(self, structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):
         dev = device(dev)
+        self.atoms = AtomTable(structure, debye_waller_factors, scattering_params, dev)
+        self._set_rows(hkl, xyz, dev)
+
+    def _set_rows(self, hkl, xyz, dev):
+        self._live = {}   # extinct_rel_cut -> plan over the rows that can pass the minimum-intensity cut
+        self.rows = None  # set on such a sub-plan: its rows' indices in the enumerated g set
         self.hkl = np.ascontiguousarray(hkl)
         self.xyz_host = np.ascontiguousarray(np.asarray(xyz, float))
         gnorm = np.sqrt((self.xyz_host ** 2).sum(axis=1))
         self.g_max = float(gnorm.max()) if gnorm.size else 0.0
-        self.atoms = AtomTable(structure, debye_waller_factors, scattering_params, dev)
         self.hkl_d = torch.as_tensor(self.hkl.astype(float), device=dev)
         self.gnorm_d = torch.as_tensor(gnorm, device=dev)
         self.xyz_d = torch.as_tensor(self.xyz_host, device=dev)
@@ -213,9 +219,33 @@ class GTablePlan:
             self.lines = (torch.as_tensor(g0, device=dev), torch.as_tensor(starts_p, device=dev),
                           np.ascontiguousarray(step, dtype=np.float64), len(starts) - 1)
 
-    def run(self, extinct_rel_cut=0.0):
-        """``extinct_rel_cut`` > 0 (and a table that ends with the direct beam): rows whose |F|^2 is below that
-        fraction of |F(000)|^2 are marked extinct for the cull of K2 (see ds_pack_gtable in the header)."""
+    def run(self, extinct_rel_cut=0.0, compact=True):
+        """``extinct_rel_cut`` > 0 (and a table that ends with the direct beam): rows whose |F|^2 is at most that
+        fraction of |F(000)|^2 can never pass the minimum-intensity cut (see ds_pack_gtable in the header for the
+        argument) and are left out.  ``compact=True`` drops them from the plan -- one synchronising analysis pass
+        per (plan, cut), after which K1 and K2 only ever see the live rows (13/16 of a diamond-cubic table is
+        systematically absent); ``compact=False`` keeps the table and marks them for K2's cull instead."""
+        if compact and extinct_rel_cut > 0.0 and self.hkl.shape[0] and not np.any(self.hkl[-1]):
+            return self._live_plan(float(extinct_rel_cut))._run(0.0)
+        return self._run(extinct_rel_cut)
+
+    def _live_plan(self, rel):
+        sub = self._live.get(rel)
+        if sub is None:
+            I0 = self._run(0.0).I0.cpu().numpy()
+            live = ~(I0 <= rel * I0[-1])          # same rule as the marking; NaN rows stay
+            if live.mean() > 0.75:
+                # few extinct rows: keep the table (and its lattice-line structure) and mark them for the cull
+                sub = _MarkedPlan(self, rel)
+            else:
+                sub = object.__new__(GTablePlan)
+                sub.atoms = self.atoms
+                sub._set_rows(self.hkl[live], self.xyz_host[live], self.xyz_d.device)
+                sub.rows = np.nonzero(live)[0]
+            self._live[rel] = sub
+        return sub
+
+    def _run(self, extinct_rel_cut=0.0):
         n = self.xyz_d.shape[0]
         dev = self.xyz_d.device
         I0 = torch.empty((n,), dtype=torch.float64, device=dev)
@@ -227,10 +257,20 @@ class GTablePlan:
                                                    _cabi.ptr(I0) if mark else None, n - 1 if mark else -1,
                                                    float(extinct_rel_cut) if mark else 0.0), "ds_pack_gtable")
         gt = GTable(hkl=self.hkl, xyz_host=self.xyz_host, xyz=self.xyz_d, f32=f32, I0=I0, g_max=self.g_max,
-                    marked=bool(mark))
+                    marked=bool(mark), rows=self.rows)
         if self.lines is not None:
             gt.line_g0, gt.line_start, gt.line_step, gt.n_lines = self.lines
         return gt
+
+
+class _MarkedPlan:
+    """A plan whose extinct rows are marked at pack time instead of being dropped (see GTablePlan.run)."""
+
+    def __init__(self, plan, rel):
+        self.plan, self.rel = plan, rel
+
+    def _run(self, _unused=0.0):
+        return self.plan._run(self.rel)
 
 
 def make_gtable(structure, hkl, xyz, debye_waller_factors, scattering_params, dev=None):

@@ -398,35 +398,39 @@ def test_render_tensor_path_accuracy(eng, monkeypatch):
                                                     ("fe3c", 1.5, "lorentzian", 1e-2), ("fe_bcc", 2.0, "atanc", 1e-4),
                                                     ("triclinic", 1.2, "binary", 0.2)])
 def test_extinction_marking_is_exact(eng, monkeypatch, name, rr, model, min_int):
-    """ds_pack_gtable's extinction marking (rows that can never pass minimum_intensity are rejected by the float32
-    cull) changes nothing but the work: same reflections, same order, same numbers -- in the brute-force and the
-    scan-line cull, for cuts from 1e-20 (systematic absences only) up to 0.2 (most of the pattern)."""
+    """Rows that can never pass minimum_intensity are either dropped from the plan (compact=True, the default) or
+    marked for K2's float32 cull (compact=False, ds_pack_gtable).  Both change nothing but the work: same
+    reflections, same order, same numbers -- in the brute-force and the scan-line cull, for cuts from 1e-20
+    (systematic absences only) up to 0.2 (most of the pattern)."""
     import diffsims_b200 as ds
-    phase = cases.phase(name)
     from diffsims_b200.utils import shape_factor_models as sfm
+    phase = cases.phase(name)
     # (the reference accepts "binary" only as a callable)
     gen = ds.SimulationGenerator(200, shape_factor_model=sfm.binary if model == "binary" else model,
                                  minimum_intensity=min_int)
     assert gen._extinct_rel_cut(True) == pytest.approx(0.5 * min_int) and gen._extinct_rel_cut(False) == 0.0
     plan = gen._g_plan(phase, rr, True, {})
+    rel = gen._extinct_rel_cut(True)
     q = random_quats(96, 4)
     q[0] = (1, 0, 0, 0)
     res = {}
     for lines in ("0", "1"):
         monkeypatch.setenv("DS_SIM_LINES", lines)
-        for marked in (False, True):
-            gt = plan.run(gen._extinct_rel_cut(True) if marked else 0.0)
+        for mode in ("full", "marked", "compact"):
+            gt = plan.run(0.0) if mode == "full" else plan.run(rel, compact=(mode == "compact"))
             n_dead = int(torch_isinf_count(gt.f32))
-            assert (n_dead > 0) == marked
-            res[lines, marked] = eng.simulate(gt, q, gen.wavelength, 0.02, 0.02, model, min_intensity=min_int,
-                                              want_exc=True)
-    ref = res["0", False]
+            assert (n_dead > 0) == (mode == "marked")
+            assert (gt.n < plan.hkl.shape[0]) == (mode == "compact")
+            res[lines, mode] = (gt, eng.simulate(gt, q, gen.wavelength, 0.02, 0.02, model, min_intensity=min_int,
+                                                 want_exc=True))
+    gt0, ref = res["0", "full"]
     assert int(ref.count.sum()) > 0
-    for key, sp in res.items():
+    for key, (gt, sp) in res.items():
         assert np.array_equal(sp.count.cpu().numpy(), ref.count.cpu().numpy()), key
         for r in range(len(q)):
             n = int(ref.count[r])
-            assert np.array_equal(sp.g_index[r, :n].cpu().numpy(), ref.g_index[r, :n].cpu().numpy()), (key, r)
+            assert np.array_equal(gt.hkl[sp.g_index[r, :n].cpu().numpy()],
+                                  gt0.hkl[ref.g_index[r, :n].cpu().numpy()]), (key, r)
             for field in ("xyz", "intensity", "exc"):
                 x, y = getattr(sp, field)[r, :n].cpu().numpy(), getattr(ref, field)[r, :n].cpu().numpy()
                 assert np.allclose(x, y, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(y).max())), (key, r, field)

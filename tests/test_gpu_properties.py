@@ -91,7 +91,10 @@ def _check_library(phase, kv, rr, s_max, n_rot, seed, shape=(256, 256), sigma=10
                 G = K.quat_to_matrix(qa).T
                 ref = K.simulate_rotation(phase.structure, gs, G, gen.wavelength, s_max, debye_waller_factors=dw)
                 n = int(spots.count[r])
-                got = dict(g_index=spots.g_index[r, :n].cpu().numpy(), xyz=spots.xyz[r, :n].cpu().numpy(),
+                gi = spots.g_index[r, :n].cpu().numpy()
+                if b.gtable.rows is not None:      # the builder's table keeps the non-extinct rows only
+                    gi = b.gtable.rows[gi]
+                got = dict(g_index=gi, xyz=spots.xyz[r, :n].cpu().numpy(),
                            intensity=spots.intensity[r, :n].cpu().numpy(), excitation_error=np.zeros(n))
                 compare_spots(ref, got, s_max=-1, rr=rr, prec=True)
                 ref_img = K.diffraction_pattern(ref["xyz"], ref["intensity"], shape, sigma=sigma, calibration=cal)

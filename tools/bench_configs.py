@@ -54,6 +54,6 @@ for name, ph, kv, rr, s_max, model, sigma, scale in CONFIGS:
     t3 = timeit(lambda: b.render(sp, img))
     natoms = len(phase.structure)
     gbs = n * 262144 / t3 / 1e6
-    print(f"{name:24s} n_g={b.gtable.n:6d} atoms={natoms:3d} n={n:6d} cap={b.cap:4d} spots/t={sp.count.float().mean().item():6.1f} | "
+    print(f"{name:24s} n_g={b.plan.hkl.shape[0]:6d} live={b.gtable.n:6d} atoms={natoms:3d} n={n:6d} cap={b.cap:4d} spots/t={sp.count.float().mean().item():6.1f} | "
           f"K1 {t1*1e3:8.1f} us ({b.gtable.n*natoms/t1/1e6:7.2f} Gpair/s) | K2 {t2*1e3:8.1f} us ({n/t2/1e3:7.2f} Mrot/s) | "
           f"K3 {t3*1e3:8.1f} us ({n/t3/1e3:6.2f} Mtmpl/s, {gbs:5.0f} GB/s = {gbs/PEAK:5.1%})")
