@@ -356,3 +356,21 @@ def test_sphere_mesh_vertices_match_reference(golden_dir):
     with pytest.raises(ValueError):
         smg.get_icosahedral_mesh_vertices(90)
     assert smg._max_neighbour_angle(np.array([[1.0, 0, 0], [0, 1, 0], [0, 1, 1], [1, 0, 1]])) == pytest.approx(45.0)  # :84-112
+
+
+def test_header_and_ctypes_signatures_agree():
+    """Every entry point declared in include/diffsims_b200.h is bound with the same number of arguments."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    header = re.sub(r"/\*.*?\*/", "", (root / "include" / "diffsims_b200.h").read_text(), flags=re.S)
+    binding = (root / "diffsims_b200" / "_cabi.py").read_text()
+    decls = re.findall(r"\b(?:int|int64_t|int32_t|const char \*)\s*\*?\s*(ds_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert {n for n, _ in decls} == set(_cabi.SYMBOLS)
+    for name, args in decls:
+        n = 0 if args.strip() in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        m = re.search(rf"L\.{name}\.argtypes = \[(.*?)\]", binding)
+        if n == 0:
+            assert m is None
+        else:
+            assert m is not None and len(m.group(1).split(",")) == n, name
