@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 MODELS = ["lorentzian", "linear", "sinc", "sin2c", "atanc", "binary"]
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(40))
 def test_random_configuration_matches_oracle(seed):
     import torch
     if not torch.cuda.is_available():
