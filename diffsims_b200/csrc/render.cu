@@ -25,7 +25,7 @@ namespace ds {
 int launch_render_pipelined(RenderParams p, cudaStream_t st);
 
 // A "group" of G warps (G = 1, 2, 4 or 8) owns one template at a time; a CTA holds 8 / G groups and is
-// persistent (loops over templates with a grid stride).  G = 1 keeps 8 independent templates in flight per
+// persistent (templates are drawn from a global ticket).  G = 1 keeps 8 independent templates in flight per
 // CTA with no block-wide barriers at all (sparse patterns are latency-, not throughput-bound); larger G
 // spreads the regions of one dense template over more warps.  Groups synchronise on named barriers.
 template <int G>

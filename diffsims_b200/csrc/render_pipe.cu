@@ -1,4 +1,5 @@
-// K3, pipelined variant for sparse patterns (the BASELINE headline case).
+// K3, pipelined variant: row capacities up to 512 (the BASELINE headline case and every library whose slots fit
+// in shared memory).
 //
 // Same arithmetic as render_kernel<FAST> (render.cu); different schedule.  In render_kernel all warps of a
 // group walk through the phases of a template together (load spots -> project / dedupe -> region bounds ->
@@ -9,9 +10,11 @@
 //                       hash, compaction -> region upper bounds -> max pass over the few regions that can hold
 //                       the maximum -> scale; publishes a slot and arrives on its `full` mbarrier;
 //   render warps        drain slot k: regions are handed out by a shared-memory ticket, each region is
-//                       accumulated in registers and streamed out with st.global.cs.v4; every warp arrives on
+//                       accumulated in registers and streamed out with st.global.cs.v4; every lane arrives on
 //                       the slot's `empty` mbarrier when the ticket runs out.
-// Two slots per CTA, so stores of template k overlap the whole preparation of template k+1.
+// Two slots per front warp, so stores of template k overlap the whole preparation of template k+1.
+// DENSE instantiations carry the tensor-core path of accumulate_region (render_device.cuh) for libraries with
+// hundreds of reflections per template; sparse libraries run the lean ones.
 #include "render_device.cuh"
 
 namespace ds {
