@@ -41,7 +41,7 @@ def lib():
     L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P]
     L.ds_pack_gtable.argtypes = [P, I, P, P, P, I, D]
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
-    L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P]
+    L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P, D]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
     L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]
     L.ds_beam_grid.argtypes = [P, I, I, P, I, P, D, P, P, P, P]

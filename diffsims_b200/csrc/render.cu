@@ -385,7 +385,8 @@ static int launch_render(const RenderParams &p, int group_bytes, size_t lut_byte
 extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const double *xyz,
                          const double *intensity, int32_t H, int32_t W, double calibration, double cx, double cy,
                          double in_plane_angle_deg, int32_t mirrored, int32_t fast, double sigma, int32_t radius,
-                         double clip_threshold, int32_t normalize, float *images, int32_t *ticket) {
+                         double clip_threshold, int32_t normalize, float *images, int32_t *ticket,
+                         double mean_spots_hint) {
     using namespace ds;
     DS_REQUIRE(n_tmpl >= 0 && cap > 0 && H > 0 && W > 0, "ds_render: bad sizes");
     DS_REQUIRE(H < 16384 && W < 16384, "ds_render: image larger than 16383 px per side");
@@ -415,6 +416,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     p.normalize = normalize;
     p.images = images;
     p.ticket = ticket;
+    p.mean_spots_hint = mean_spots_hint;
     p.table_size = 0;
     p.n4 = 0;
     p.hits_bytes = 0;

@@ -41,6 +41,7 @@ struct RenderParams {
     int mma_tmpl_min;  // spots per template from which regions are examined for it
     float *images;
     int *ticket;  // [2] device scratch, zero on entry and on exit: dynamic template assignment
+    double mean_spots_hint;  // caller's estimate of the mean reflections per template (<= 0: unknown)
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -316,8 +316,10 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     if (p.cap > pipe_max_cap() || n_regions > 1024 || p.radius >= p.W || p.radius >= p.H) return 0;
     const int slot_bytes = (32 + p.cap * 8 + n_regions + 15) & ~15;
     const int front_bytes = (int)((p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 + (size_t)p.cap * 8);
-    // one front warp keeps up with the sparsest patterns; above 32 reflections per template two share the work
-    int nf = p.cap <= 32 ? 1 : 2;
+    // Two front warps by default.  One keeps up only with the sparsest libraries (measured at 256 x 256, sigma 10,
+    // normalised, capacity 32: 3.8 reflections per template 1258 us with one front vs 1273 with two, but 11.3
+    // reflections 1611 vs 1277), so it takes the caller's word that the library is that sparse.
+    int nf = (p.cap <= 32 && p.mean_spots_hint > 0.0 && p.mean_spots_hint < 6.0) ? 1 : 2;
     if (const char *e = getenv("DS_RENDER_FRONTS")) nf = min(max(atoi(e), 1), 3);
     const size_t smem = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
     if (smem > 96 * 1024) return 0;

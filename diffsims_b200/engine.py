@@ -369,10 +369,11 @@ def gaussian_radius(sigma, truncate=4.0):
 
 
 def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_angle=0.0, mirrored=False,
-           fast=True, normalize=True, clip_threshold=1.0, out=None):
+           fast=True, normalize=True, clip_threshold=1.0, out=None, mean_spots=None):
     """Run K3. ``count`` [n] int32, ``xyz`` [n,cap,3] f64, ``intensity`` [n,cap] f64 device tensors.
     ``fast``: True = integer-pixel branch, False = sub-pixel branch on the in-frame spots, "bare" = sub-pixel
-    branch without the in-frame selection (detector_functions.get_pattern_from_pixel_coordinates_and_intensities)."""
+    branch without the in-frame selection (detector_functions.get_pattern_from_pixel_coordinates_and_intensities).
+    ``mean_spots``: the mean of ``count`` if the caller knows it without synchronising (a schedule hint only)."""
     dev = xyz.device
     n, cap = intensity.shape
     H, W = int(shape[0]), int(shape[1])
@@ -384,7 +385,7 @@ def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_an
         _stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), _cabi.ptr(intensity), H, W,
         float(calibration), float(center[0]), float(center[1]), float(in_plane_angle), int(bool(mirrored)),
         (2 if fast == "bare" else int(bool(fast))), float(sigma), gaussian_radius(sigma), float(clip_threshold), int(bool(normalize)),
-        _cabi.ptr(out), _cabi.ptr(_ticket(dev)))
+        _cabi.ptr(out), _cabi.ptr(_ticket(dev)), 0.0 if mean_spots is None else float(mean_spots))
     _cabi.check(rc, "ds_render")
     return out
 

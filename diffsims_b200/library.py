@@ -66,6 +66,7 @@ class TemplateLibraryBuilder:
         self.gtable = None
         self.plan = None   # host enumeration + uploads of the phase, made once
         self.launches = 0  # kernels of libdiffsims_b200.so launched by this builder
+        self.mean_spots = None  # mean reflections per template seen by calibrate_cap (schedule hint for K3)
 
     # -- K1 ----------------------------------------------------------------------------------------
     def prepare(self):
@@ -91,7 +92,8 @@ class TemplateLibraryBuilder:
     def render(self, spots, out):
         self.launches += 1
         return engine.render(spots.count, spots.xyz, spots.intensity, self.shape, self.sigma, self.calibration,
-                             self.center, self.angle, self.mirrored, self.fast, self.normalize, self.clip, out=out)
+                             self.center, self.angle, self.mirrored, self.fast, self.normalize, self.clip, out=out,
+                             mean_spots=self.mean_spots)
 
     def calibrate_cap(self, quats_dev):
         """One untimed overflow-checked pass that fixes ``cap`` for the rotation list."""
@@ -100,6 +102,7 @@ class TemplateLibraryBuilder:
         # minimum-intensity cut (K2 compacts in place); the later unchecked passes rely on this capacity
         need = int(spots.max_count.item()) if spots.n_rot and spots.max_count is not None else 0
         self.cap = max(32, (max(need, 1) + 31) // 32 * 32)
+        self.mean_spots = float(spots.count.float().mean().item()) if spots.n_rot else None
         return self.cap
 
     def assert_no_overflow(self, spots):

@@ -153,7 +153,9 @@ int ds_render(void *stream,
               double clip_threshold, int32_t normalize,
               float *images /*[n_tmpl][H][W]*/,
               int32_t *ticket /*[2] device scratch: zero before the first call, left zero by every call; one
-                                 per concurrently used stream (templates are handed to CTAs dynamically)*/);
+                                 per concurrently used stream (templates are handed to CTAs dynamically)*/,
+              double mean_spots_hint /*expected reflections per template, <= 0 if unknown: only tunes the
+                                       schedule (front warps per CTA), never the result*/);
 
 /*
  * Polar flattening of the packed result for template matching.

@@ -38,7 +38,7 @@ def test_abi_argument_validation_without_gpu():
     rc = lib.ds_simulate(None, 4, None, 10, None, None, None, 1.0, 40.0, 0.01, 0.01, 99, 5.0, 0.0, 1e-20, 32,
                          None, None, None, None, None, None, 0, None, None, None)
     assert rc != 0 and b"shape model" in lib.ds_last_error()
-    rc = lib.ds_render(None, 1, 32, None, None, None, 64, 64, 0.0, 32.0, 32.0, 0.0, 0, 1, 2.0, 8, 1.0, 1, None, None)
+    rc = lib.ds_render(None, 1, 32, None, None, None, 64, 64, 0.0, 32.0, 32.0, 0.0, 0, 1, 2.0, 8, 1.0, 1, None, None, 0.0)
     assert rc != 0 and b"calibration" in lib.ds_last_error()
     rc = lib.ds_structure_factors(None, 4, None, None, 1, None, None, 1, None, None, None, 7, None, None, None)
     assert rc != 0 and b"scattering" in lib.ds_last_error()
