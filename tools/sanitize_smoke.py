@@ -41,6 +41,12 @@ os.environ["DS_SIM_LINES"] = "1"
 gt = gen._g_table(cases.phase("si"), 2.0, True, cases.DW)
 engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian")
 engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian_precession", precession_rad=0.0087)
+# extinct rows marked in the packed table (compact=False), culled by the plain and by the scan-line loop
+plan = gen._g_plan(cases.phase("si"), 2.0, True, {})
+for lines in ("0", "1"):
+    os.environ["DS_SIM_LINES"] = lines
+    engine.simulate(plan.run(0.5e-20, compact=False), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
+engine.simulate(plan.run(0.5e-20), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 os.environ.pop("DS_SIM_LINES", None)
 from diffsims_b200.pattern.detector_functions import get_pattern_from_pixel_coordinates_and_intensities
 get_pattern_from_pixel_coordinates_and_intensities(rng.uniform(-8, 98, (40, 2)), rng.uniform(20, 900, 40), (70, 90), 2.5)
