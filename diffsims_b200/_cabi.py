@@ -11,10 +11,10 @@ _LIB_PATH = Path(__file__).resolve().parent / "libdiffsims_b200.so"
 _lib = None
 
 # every symbol include/diffsims_b200.h declares
-SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_structure_factors", "ds_pack_gtable",
+SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors", "ds_pack_gtable",
            "ds_simulate", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
            "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeLibraryError(ImportError):
@@ -48,6 +48,8 @@ def lib():
     L.ds_beam_grid_num_blocks.argtypes = [I]
     L.ds_beam_points.argtypes = [P, I, ctypes.c_int64, P, I, P, D, P, P, P, P]
     L.ds_beam_points_num_blocks.argtypes = [ctypes.c_int64]
+    L.ds_set_option.argtypes = [c_char_p, I]
+    L.ds_get_option.argtypes = [c_char_p, P]
     for s in SYMBOLS[2:]:
         getattr(L, s).restype = c_int32
     L.ds_beam_grid_num_blocks.restype = ctypes.c_int64
@@ -64,3 +66,14 @@ def check(rc, what):
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else c_void_p(t.data_ptr())
+
+
+def set_option(name, value):
+    """Process-wide schedule option of the native library (see include/diffsims_b200.h); -1 = default."""
+    check(lib().ds_set_option(name.encode(), int(value)), "ds_set_option")
+
+
+def get_option(name):
+    v = c_int32(0)
+    check(lib().ds_get_option(name.encode(), ctypes.byref(v)), "ds_get_option")
+    return v.value

@@ -9,6 +9,26 @@
 namespace ds {
 
 void set_error(const char *fmt, ...);
+int num_sms();  // of the current device (queried per call: one process may drive several GPUs)
+
+// Process-wide tuning options (cabi.cu): read from the environment once, changed with ds_set_option.
+// -1 = not set.
+enum Opt {
+    OPT_RENDER_PIPE = 0,
+    OPT_RENDER_GROUP,
+    OPT_RENDER_FRONTS,
+    OPT_RENDER_PIPE_MAXCAP,
+    OPT_RENDER_NOSTAGE,
+    OPT_RENDER_MMA,
+    OPT_RENDER_MMA_MIN,
+    OPT_RENDER_MMA_TMPL_MIN,
+    OPT_RENDER_UMMA,
+    OPT_RENDER_UMMA_WINDOW,
+    OPT_SIM_LINES,
+    OPT_SIM_SPLIT,
+    OPT_COUNT
+};
+int option(Opt o);
 
 inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -59,18 +79,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
         : "memory");
+    return ok != 0;
+}
+// Waits are bounded: a barrier that does not complete within ~10^10 cycles (seconds) is a protocol bug, and the
+// kernel traps (the launch fails loudly with a sticky error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    if (mbar_try(bar, phase)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, phase))
+        if (clock64() - t0 > 10000000000ll) __trap();
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

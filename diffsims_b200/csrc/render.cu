@@ -23,6 +23,7 @@
 namespace ds {
 
 int launch_render_pipelined(RenderParams p, cudaStream_t st);
+int launch_render_umma(RenderParams p, cudaStream_t st);
 
 // A "group" of G warps (G = 1, 2, 4 or 8) owns one template at a time; a CTA holds 8 / G groups and is
 // persistent (templates are drawn from a global ticket).  G = 1 keeps 8 independent templates in flight per
@@ -366,11 +367,9 @@ static int launch_render(const RenderParams &p, int group_bytes, size_t lut_byte
     const size_t smem = lut_bytes + (size_t)NGROUPS * group_bytes;
     DS_REQUIRE(smem <= 200 * 1024, "ds_render: cap=%d / radius=%d need %zu bytes of shared memory", p.cap, p.radius,
                smem);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(render_kernel<FAST, G, WIDE, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
+    // (set on every launch: the attribute is per device, and a cached flag would be a data race between streams)
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(render_kernel<FAST, G, WIDE, VEC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FAST, G, WIDE, VEC, DENSE>, RN_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
@@ -444,12 +443,12 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
         // because of the list building in front of mostly sparse regions).
         p.hits_bytes = 0;
         p.mma_min = MMA_MIN_HITS;
-        if (const char *e = getenv("DS_RENDER_MMA_MIN")) p.mma_min = atoi(e) > 1 ? atoi(e) : MMA_MIN_HITS;
+        if (option(OPT_RENDER_MMA_MIN) > 1) p.mma_min = option(OPT_RENDER_MMA_MIN);
         const double frac = fmin(1.0, (2.0 * radius + 1 + RN_RW) * (2.0 * radius + 1 + RN_RH) / ((double)W * H));
         p.mma_tmpl_min = (int)ceil(p.mma_min / frac);
-        if (const char *e = getenv("DS_RENDER_MMA_TMPL_MIN")) p.mma_tmpl_min = atoi(e);
-        const char *force = getenv("DS_RENDER_MMA");
-        const bool want = force ? atoi(force) != 0 : cap >= 3 * p.mma_tmpl_min;
+        if (option(OPT_RENDER_MMA_TMPL_MIN) >= 0) p.mma_tmpl_min = option(OPT_RENDER_MMA_TMPL_MIN);
+        const int force = option(OPT_RENDER_MMA);
+        const bool want = force >= 0 ? force != 0 : cap >= 3 * p.mma_tmpl_min;
         if (want && !wide && cap >= p.mma_min && cap <= 4096)
             p.hits_bytes = RN_WARPS * ((2 * cap * 2 + 15) & ~15);  // 2 cap entries: spots + their reflect images
         lut_bytes = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes;
@@ -462,20 +461,30 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
                (reinterpret_cast<uintptr_t>(intensity) & 15) == 0)
                   ? 1
                   : 0;
-    if (getenv("DS_RENDER_NOSTAGE")) p.stage = 0;
+    if (option(OPT_RENDER_NOSTAGE) > 0) p.stage = 0;
     if (p.stage) group_bytes += 2 * cap * 32;
     const int group_fixed = (group_bytes + 15) & ~15;  // + flags and per-warp bound partials, which depend on G
     // warps per template, measured on B200 (tools/bench_configs.py): sparse patterns (<= 32 reflections) are
     // write-bound and like the whole CTA on one template (one 256 KB window per CTA); denser ones are
     // phase/latency-bound and like more templates in flight per SM.  DS_RENDER_GROUP overrides.
     int G = cap <= 32 ? 8 : (cap <= 64 ? 4 : 2);
-    if (const char *e = getenv("DS_RENDER_GROUP")) {
-        const int g = atoi(e);
-        if (g == 1 || g == 2 || g == 4 || g == 8) G = g;
+    const int g_opt = option(OPT_RENDER_GROUP);
+    const bool g_forced = g_opt == 1 || g_opt == 2 || g_opt == 4 || g_opt == 8;
+    if (g_forced) G = g_opt;
+    // The ticket words start every launch at zero (a launch that died mid-way cannot poison the next one).
+    cudaMemsetAsync(ticket, 0, 2 * sizeof(int32_t), st);
+    // Templates of up to 256 x 256 px with more than a handful of reflections: the tcgen05 kernel (render_umma.cu);
+    // option render_umma = 0 / 1 forces it off / on.  Measured cross-over on B200: see DESIGN.md.
+    if (fast && !wide && !g_forced) {
+        const int um = option(OPT_RENDER_UMMA);
+        const bool want_umma = um >= 0 ? um != 0 : (cap > 32 || mean_spots_hint >= 12.0);
+        if (want_umma) {
+            const int rc = launch_render_umma(p, st);
+            if (rc != 0) return rc < 0 ? rc : 0;
+        }
     }
-    // sparse patterns take the warp-specialised pipelined kernel (render_pipe.cu); DS_RENDER_PIPE=0 disables
-    if (fast && !wide && !(getenv("DS_RENDER_PIPE") && atoi(getenv("DS_RENDER_PIPE")) == 0) &&
-        !getenv("DS_RENDER_GROUP")) {
+    // sparse patterns take the warp-specialised pipelined kernel (render_pipe.cu); render_pipe = 0 disables
+    if (fast && !wide && option(OPT_RENDER_PIPE) != 0 && !g_forced) {
         const int rc = launch_render_pipelined(p, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }

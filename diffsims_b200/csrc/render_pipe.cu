@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
 }
 
 static int pipe_max_cap() {
-    const char *e = getenv("DS_RENDER_PIPE_MAXCAP");
-    return e ? atoi(e) : 512;  // beyond that (or when the slots do not fit in shared memory): render_kernel
+    const int e = option(OPT_RENDER_PIPE_MAXCAP);
+    return e >= 0 ? e : 512;  // beyond that (or when the slots do not fit in shared memory): render_kernel
 }
 
 // Returns 1 if the pipelined kernel was launched, 0 if the configuration is not eligible, < 0 on error.
@@ -320,7 +320,7 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     // normalised, capacity 32: 3.8 reflections per template 1258 us with one front vs 1273 with two, but 11.3
     // reflections 1611 vs 1277), so it takes the caller's word that the library is that sparse.
     int nf = (p.cap <= 32 && p.mean_spots_hint > 0.0 && p.mean_spots_hint < 6.0) ? 1 : 2;
-    if (const char *e = getenv("DS_RENDER_FRONTS")) nf = min(max(atoi(e), 1), 3);
+    if (option(OPT_RENDER_FRONTS) > 0) nf = min(max(option(OPT_RENDER_FRONTS), 1), 3);
     const size_t smem = lut_smem_bytes(p.n4) + (size_t)p.hits_bytes + (size_t)nf * front_bytes + (size_t)2 * nf * slot_bytes;
     if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
@@ -334,12 +334,7 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
          {render_pipe_kernel<false, 3, true>, render_pipe_kernel<true, 3, true>}}};
     const int dense = p.hits_bytes > 0 ? 1 : 0;
     void (*kern)(RenderParams, int, int) = kerns[dense][nf - 1][vec ? 1 : 0];
-    static bool attr[12] = {false};
-    const int slot_id = dense * 6 + (nf - 1) * 2 + (vec ? 1 : 0);
-    if (smem > 48 * 1024 && !attr[slot_id]) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr[slot_id] = true;
-    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RN_THREADS, smem);
     if (per_sm < 1) per_sm = 1;

@@ -495,17 +495,6 @@ __global__ void pack_gtable_kernel(int n_g, const double *__restrict__ g, float4
     }
 }
 
-static int g_num_sms = 0;
-int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
-
 }  // namespace ds
 
 extern "C" int ds_pack_gtable(void *stream, int32_t n_g, const double *g_xyz, float *g_f32, const double *g_I0,
@@ -570,9 +559,9 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         const double slab = 2.0 * s_max + rs - sqrt(rs * rs - gm * gm) + 2.0 * rs * sin(fabs(precession_rad)) * gm / rs;
         const double step = sqrt(line_step_host[0] * line_step_host[0] + line_step_host[1] * line_step_host[1] +
                                  line_step_host[2] * line_step_host[2]);
-        const char *force = getenv("DS_SIM_LINES");
-        if (force)
-            lines = atoi(force) != 0;
+        const int force = option(OPT_SIM_LINES);
+        if (force >= 0)
+            lines = force != 0;
         else
             lines = n_g >= 2048 && slab < 0.5 * step;
     }
@@ -612,11 +601,9 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // no precession: one lean kernel per shape factor model; anything with precession: the general kernel
     auto launch = [&](auto kern, int slot) {
-        static bool attr_set[18] = {false};
-        if (!attr_set[slot]) {
+        (void)slot;
+        if (smem > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
-            attr_set[slot] = true;
-        }
         int blocks_per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SIM_THREADS, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;

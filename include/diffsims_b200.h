@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 1
+#define DS_ABI_VERSION 2
 
 /* atomic scattering factor parameterisations, diffsims/utils/sim_utils.py:227-253 */
 #define DS_SCATT_NONE    0 /* f = 1 for every atom (sim_utils.py:284-286)          */
@@ -45,6 +45,28 @@ extern "C" {
 
 int ds_abi_version(void);
 const char *ds_last_error(void);
+
+/*
+ * Process-wide tuning options (schedules only, never results).  Each option also has an environment variable
+ * that is read ONCE, at the first use of the library; launch paths afterwards only do atomic loads, so
+ * launches on different streams / host threads never race.  value -1 = "not set" (the measured default).
+ *   render_pipe (DS_RENDER_PIPE) 0: K3 without the warp-specialised pipelined kernel
+ *   render_group (DS_RENDER_GROUP) 1/2/4/8: warps per template of the phase-synchronous K3 kernel
+ *   render_fronts (DS_RENDER_FRONTS) 1..3: preparation warps of the pipelined K3 kernel
+ *   render_pipe_maxcap (DS_RENDER_PIPE_MAXCAP): largest row capacity the pipelined K3 kernel takes
+ *   render_nostage (DS_RENDER_NOSTAGE) 1: K3 reads spot rows in place instead of cp.async.bulk staging
+ *   render_mma (DS_RENDER_MMA) 0/1, render_mma_min, render_mma_tmpl_min: legacy mma.sync path of the
+ *       phase-synchronous / pipelined kernels and its thresholds
+ *   render_umma (DS_RENDER_UMMA) 0/1: tcgen05 K3 kernel off / forced (default: by capacity and density hint)
+ *   render_umma_window (DS_RENDER_UMMA_WINDOW) 0: tcgen05 K3 kernel without per-chunk column windows
+ *   sim_lines (DS_SIM_LINES) 0/1: K2 scan-line cull off / forced
+ *   sim_split (DS_SIM_SPLIT) 0/n: K2 g-table split across CTAs off / forced to n parts
+ * Thread safety of the library: entry points may be called concurrently from several host threads as long
+ * as the calls use different streams and different output buffers (and different `ticket` words for
+ * ds_render); one process may drive several devices.
+ */
+int ds_set_option(const char *name, int32_t value);
+int ds_get_option(const char *name, int32_t *value);
 
 /*
  * K1 -- kinematical structure factors, once per (phase, g-set).
@@ -152,8 +174,8 @@ int ds_render(void *stream,
               int32_t fast, double sigma, int32_t radius,
               double clip_threshold, int32_t normalize,
               float *images /*[n_tmpl][H][W]*/,
-              int32_t *ticket /*[2] device scratch: zero before the first call, left zero by every call; one
-                                 per concurrently used stream (templates are handed to CTAs dynamically)*/,
+              int32_t *ticket /*[2] device scratch words, zeroed by the call itself on `stream`; one pair per
+                                 concurrently used stream (templates are handed to CTAs dynamically)*/,
               double mean_spots_hint /*expected reflections per template, <= 0 if unknown: only tunes the
                                        schedule (front warps per CTA), never the result*/);
 

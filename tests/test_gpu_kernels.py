@@ -127,7 +127,7 @@ def test_simulate_streaming_tiles_large_cell(eng):
     ("si", 2.0, 0.01, "lorentzian_precession", 0.5),
     ("large", 1.2, 0.01, "lorentzian", 0.0),
 ])
-def test_simulate_scan_line_cull_is_identical(eng, monkeypatch, name, rr, s_max, model, prec_deg):
+def test_simulate_scan_line_cull_is_identical(eng, opts, name, rr, s_max, model, prec_deg):
     """The scan-line cull (lattice lines solved for their slab crossing) and the brute-force cull feed the same
     candidates in the same order to the same float64 refine: identical reflection lists, including for lines
     parallel to the slab (c* in the detector plane) and zone axes."""
@@ -142,8 +142,8 @@ def test_simulate_scan_line_cull_is_identical(eng, monkeypatch, name, rr, s_max,
     q[3] = (np.cos(np.pi / 4 + 2e-4), np.sin(np.pi / 4 + 2e-4), 0, 0)   # almost parallel
     q[4] = (np.cos(np.pi / 4 + 2e-3), np.sin(np.pi / 4 + 2e-3), 0, 0)
     out = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("DS_SIM_LINES", mode)
+    for mode in (0, 1):
+        opts(sim_lines=mode)
         sp = eng.simulate(gt, q, wl, s_max, s_max, model, precession_rad=np.deg2rad(prec_deg), want_exc=True)
         out.append(sp)
     a, b = out
@@ -258,17 +258,18 @@ def test_render_graphite_golden(eng, golden_dir):
 
 
 # --------------------------------------------------------------------------- K3 schedule variants
-@pytest.mark.parametrize("variant", ["pipe", "G8", "G4", "G2", "G1"])
+@pytest.mark.parametrize("variant", ["umma", "umma_nowin", "pipe", "G8", "G4", "G2", "G1"])
 @pytest.mark.parametrize("shape,sigma", [((256, 256), 10.0), ((144, 144), 3.0), ((90, 130), 2.0)])
-def test_render_schedule_variants_agree_with_oracle(eng, monkeypatch, variant, shape, sigma):
-    """The warp-specialised pipelined kernel and every group size of the phase-synchronous kernel are the
-    same arithmetic under different schedules (130 is not a multiple of 4: scalar-store instantiation)."""
+def test_render_schedule_variants_agree_with_oracle(eng, opts, variant, shape, sigma):
+    """The tcgen05 kernel, the warp-specialised pipelined kernel and every group size of the phase-synchronous
+    kernel against the oracle (130 is not a multiple of 4: scalar-store instantiation)."""
     import torch
-    if variant == "pipe":
-        monkeypatch.delenv("DS_RENDER_GROUP", raising=False)
-        monkeypatch.setenv("DS_RENDER_PIPE", "1")
+    if variant.startswith("umma"):
+        opts(render_group=-1, render_umma=1, render_umma_window=0 if variant == "umma_nowin" else -1)
+    elif variant == "pipe":
+        opts(render_group=-1, render_pipe=1, render_umma=0)
     else:
-        monkeypatch.setenv("DS_RENDER_GROUP", variant[1:])
+        opts(render_group=int(variant[1:]), render_umma=0)
     phase = cases.phase("fe3c")
     gs = K.GSet(phase.structure, 1.2, True)
     wl = K.get_electron_wavelength(200)
@@ -339,18 +340,21 @@ def test_render_slow_path_with_many_spots(eng):
         assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
 
 
-@pytest.mark.parametrize("pipe", ["1", "0"])
+@pytest.mark.parametrize("pipe", ["umma", "1", "0"])
 @pytest.mark.parametrize("cap,sigma,normalize,shape", [
     (288, 10.0, True, (256, 256)), (288, 3.0, False, (256, 256)), (512, 6.0, True, (256, 256)),
     (1024, 2.0, True, (256, 256)), (288, 7.0, True, (96, 200)), (160, 5.0, True, (100, 150)),
     (96, 12.0, False, (40, 72))])
-def test_render_fast_path_with_many_spots(eng, monkeypatch, pipe, cap, sigma, normalize, shape):
-    """Dense patterns (hundreds of reflections per template) through both schedules: the warp-specialised kernel
-    takes capacities up to 512 while its slots fit in shared memory, render_kernel everything else.  Regions
-    reached by >= 16 spots run on the tensor cores (bf16 x 3 split products), incl. reflect images at the
-    borders, partial regions and rows that are not 16-byte multiples."""
+def test_render_fast_path_with_many_spots(eng, opts, pipe, cap, sigma, normalize, shape):
+    """Dense patterns (hundreds of reflections per template) through all schedules: the tcgen05 kernel (capacities
+    up to 1024, images up to 256 x 256), the warp-specialised kernel (capacities up to 512 while its slots fit in
+    shared memory) and render_kernel for everything else.  The tensor-core paths use bf16 x 3 split products,
+    incl. reflect images at the borders, partial tiles and rows that are not 16-byte multiples."""
     import torch
-    monkeypatch.setenv("DS_RENDER_PIPE", pipe)
+    if pipe == "umma":
+        opts(render_umma=1)
+    else:
+        opts(render_umma=0, render_pipe=int(pipe))
     rng = np.random.default_rng(cap)
     n = 5
     X = np.zeros((n, cap, 3))
@@ -373,9 +377,10 @@ def test_render_fast_path_with_many_spots(eng, monkeypatch, pipe, cap, sigma, no
             assert out[r].max() == 1.0
 
 
-def test_render_tensor_path_accuracy(eng, monkeypatch):
-    """The bf16 split-product tensor-core path against the float32 FMA path on the same dense templates: the
-    difference stays below 3e-5 of the peak (budget: 1e-4), and the normalised maximum is exactly 1 in both."""
+def test_render_tensor_path_accuracy(eng, opts):
+    """The bf16 split-product tensor-core paths (tcgen05 kernel; legacy mma.sync regions) against the float32 FMA
+    path on the same dense templates: the difference stays below 3e-5 of the peak (budget: 1e-4), and the
+    normalised maximum is exactly 1 in all of them."""
     import torch
     rng = np.random.default_rng(11)
     n, cap, shape = 4, 512, (256, 256)
@@ -386,18 +391,20 @@ def test_render_tensor_path_accuracy(eng, monkeypatch):
     args = (cnt, torch.as_tensor(X, device=eng.device()), torch.as_tensor(I, device=eng.device()), shape, 10.0,
             1 / 128, (127.5, 127.5))
     out = {}
-    for mma in ("1", "0"):
-        monkeypatch.setenv("DS_RENDER_MMA", mma)
-        out[mma] = eng.render(*args).cpu().numpy()
-    assert not np.array_equal(out["1"], out["0"])            # the tensor-core path did run
-    assert np.abs(out["1"] - out["0"]).max() < 3e-5
+    for name, kw in (("umma", dict(render_umma=1)), ("mma", dict(render_umma=0, render_mma=1)),
+                     ("fma", dict(render_umma=0, render_mma=0))):
+        opts(**kw)
+        out[name] = eng.render(*args).cpu().numpy()
+    for name in ("umma", "mma"):
+        assert not np.array_equal(out[name], out["fma"])            # the tensor-core path did run
+        assert np.abs(out[name] - out["fma"]).max() < 3e-5, name
     assert all(o[r].max() == 1.0 for o in out.values() for r in range(n))
 
 
 @pytest.mark.parametrize("name,rr,model,min_int", [("si", 2.0, "lorentzian", 1e-20), ("al", 2.0, "linear", 1e-20),
                                                     ("fe3c", 1.5, "lorentzian", 1e-2), ("fe_bcc", 2.0, "atanc", 1e-4),
                                                     ("triclinic", 1.2, "binary", 0.2)])
-def test_extinction_marking_is_exact(eng, monkeypatch, name, rr, model, min_int):
+def test_extinction_marking_is_exact(eng, opts, name, rr, model, min_int):
     """Rows that can never pass minimum_intensity are either dropped from the plan (compact=True, the default) or
     marked for K2's float32 cull (compact=False, ds_pack_gtable).  Both change nothing but the work: same
     reflections, same order, same numbers -- in the brute-force and the scan-line cull, for cuts from 1e-20
@@ -415,7 +422,7 @@ def test_extinction_marking_is_exact(eng, monkeypatch, name, rr, model, min_int)
     q[0] = (1, 0, 0, 0)
     res = {}
     for lines in ("0", "1"):
-        monkeypatch.setenv("DS_SIM_LINES", lines)
+        opts(sim_lines=int(lines))
         for mode in ("full", "marked", "compact"):
             gt = plan.run(0.0) if mode == "full" else plan.run(rel, compact=(mode == "compact"))
             n_dead = int(torch_isinf_count(gt.f32))
