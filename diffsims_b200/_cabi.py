@@ -7,7 +7,10 @@ import ctypes
 from ctypes import c_char_p, c_double, c_int32, c_void_p
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libdiffsims_b200.so"
+import os
+
+# (DIFFSIMS_B200_LIB: an instrumented build of the same sources, used by tools/ only)
+_LIB_PATH = Path(os.environ.get("DIFFSIMS_B200_LIB") or Path(__file__).resolve().parent / "libdiffsims_b200.so")
 _lib = None
 
 # every symbol include/diffsims_b200.h declares

@@ -84,12 +84,12 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
+        : "r"(smem_u32(bar)), "r"(phase), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of
+        : "memory");                                       // polling (polls would compete with the working warps' LDS / STS)
     return ok != 0;
 }
 // Waits are bounded: a barrier that does not complete within ~10^10 cycles (seconds) is a protocol bug, and the

@@ -13,34 +13,40 @@
 //   * after the first chunk of a half (which covers, and thereby zeroes, all columns) a chunk only spans the
 //     16-column-aligned window its spots reach: N is a per-instruction field, and the front warp sorts each
 //     half's spots by column so that the windows of a dense template are narrow;
-//   * four epilogue warps read the accumulators back with tcgen05.ld (lane = image row), take the template
-//     maximum from them (no second evaluation), scale, transpose 32 x 32 tiles through padded shared memory and
-//     stream them out with the same 4 rows x 128 bytes st.global.cs.v4 pattern as the other render kernels.
+//   * eight epilogue warps read the accumulators back with tcgen05.ld (lane = image row), take the template
+//     maximum from them (no second evaluation), scale, write 32 x 32 tiles to 128-byte-swizzled shared memory and
+//     hand them to the TMA engine (cp.async.bulk.tensor store through a 3-D tensor map of the image stack, which
+//     also clips partial tiles), double-buffered so that tensor-memory reads, stores and copies overlap.
 //
 // Warp roles of the persistent CTA (one per SM, templates drawn from the global ticket):
-//   warp 0        front: prefetched spot rows -> float64 projection -> last-write-wins hash -> compaction ->
-//                 per-half lists (sorted by column) -> publishes one of two template slots
+//   warp 0        front: prefetched spot rows -> float64 projection -> counting sort by column (ties in list
+//                 order) -> last-write-wins inside a pixel -> per-half lists -> publishes one of two template slots
 //   warp 1        MMA issue (lane 0), owns the tensor-memory allocation (512 columns = 2 halves x 256)
-//   warps 2..5    epilogue (tensor-memory lane quarter = warp % 4)
-//   warps 6..11   operand producers, one shared-memory stage each
+//   warps 4..11   epilogue (tensor-memory lane quarter = warp % 4; two warps per quarter share its column tiles)
+//   warps 2, 3, 12..15   operand producers: three teams of two warps, one shared-memory stage per team
 // mbarriers: slot full/empty (front <-> everyone), stage full/empty (producer <-> tcgen05.commit),
 // half full/empty (tcgen05.commit <-> epilogue).  Bound: tensor pipe for dense templates, HBM write otherwise.
 //
 // Reference: diffsims/pattern/detector_functions.py:293-300 (assignment + scipy.ndimage.gaussian_filter),
 // diffsims/simulations/simulation2d.py:261-285, :422-441.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is looked up through the runtime)
+
+#include <atomic>
+
 #include "render_device.cuh"
 
 namespace ds {
 
-constexpr int UM_NP = 6;                       // producer warps = operand stages
-constexpr int UM_EPI = 4;                      // epilogue warps
-constexpr int UM_WARPS = 2 + UM_EPI + UM_NP;   // 12
-constexpr int UM_THREADS = UM_WARPS * 32;      // 384
+constexpr int UM_NP = 3;                       // operand stages = producer teams (two warps each: K groups 0 / 1 of a chunk)
+constexpr int UM_EPI = 8;                      // epilogue warps: two per tensor-memory lane quarter
+constexpr int UM_WARPS = 2 + UM_EPI + 2 * UM_NP;  // 16: four warps per scheduler, 128 registers per thread
+constexpr int UM_THREADS = UM_WARPS * 32;      // 512
+// warp roles: 0 front, 1 MMA issue, 2-3 and 12-15 producers, 4-11 epilogue (lane quarter = warp % 4)
+constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_A_BYTES = 128 * 16 * 2;       // one of A_hi / A_lo:  16 MN groups x 2 K groups x 128 B
 constexpr int UM_B_BYTES = 256 * 16 * 2;       // one of B_hi / B_lo:  32 MN groups x 2 K groups x 128 B
 constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES;  // 24 KB
-constexpr int UM_EPI_PITCH = 36;               // floats per staged row (32 + 4: conflict-free both ways)
-constexpr int UM_EPI_BYTES = 32 * UM_EPI_PITCH * 4;
+constexpr int UM_TILE_BYTES = 32 * 32 * 4;     // one staged 32 x 32 float tile (128-byte rows, 128B swizzle)
 constexpr int UM_BPAD = 8;                     // zero padding of the bf16 tap table on either side
 constexpr int UM_MAX_CAP = 1024;
 
@@ -123,12 +129,82 @@ __device__ __forceinline__ void store_split8(uint32_t hi_addr, uint32_t lo_addr,
     sts128(lo_addr, l[0], l[1], l[2], l[3]);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const RenderParams p, const int slot_bytes,
-                                                                     const int front_bytes, const int window) {
+// tcgen05.ld without the wait (the registers are only valid after tmem_wait on the same array)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+        "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr)
+        : "memory");
+}
+// wait for all of this thread's tensor-memory loads; the array is an in/out operand so that no use of it can be
+// scheduled ahead of the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+// TMA store of one staged tile: box (32 columns, 32 rows, 1 template) at (x, y, t); rows / columns beyond the
+// image are clipped by the tensor map
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap *tmap, uint32_t smem_src, int x, int y, int t) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_src),
+                 "r"(x), "r"(y), "r"(t)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+#ifdef DS_PROF
+// per-role cycle counters of CTA 0 (profiling builds only): [role][0] = cycles in the role's loop, [1] = of which waiting
+__device__ unsigned long long g_um_prof[4][2];
+__device__ unsigned long long g_um_prof2[8];  // first epilogue warp of CTA 0: cycles per section (register accumulators)
+#define PROF_SEC_DECL long long prof_sec[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_s0 = 0
+#define PROF_SEC_BEGIN prof_s0 = clock64()
+#define PROF_SEC(i)                        \
+    {                                      \
+        const long long now_ = clock64();  \
+        prof_sec[i] += now_ - prof_s0;     \
+        prof_s0 = now_;                    \
+    }
+#define PROF_SEC_DONE                                                                 \
+    if (blockIdx.x == 0 && lane == 0)                                                 \
+        for (int i_ = 0; i_ < 8; ++i_) g_um_prof2[i_] = (unsigned long long)prof_sec[i_];
+#define PROF_DECL long long prof_t0 = clock64(), prof_wait = 0, prof_w0 = 0
+#define PROF_WAIT_BEGIN prof_w0 = clock64()
+#define PROF_WAIT_END prof_wait += clock64() - prof_w0
+#define PROF_DONE(role)                                                          \
+    if (blockIdx.x == 0 && lane == 0) {                                          \
+        g_um_prof[role][0] = (unsigned long long)(clock64() - prof_t0);          \
+        g_um_prof[role][1] = (unsigned long long)prof_wait;                      \
+    }
+#else
+#define PROF_SEC_DECL
+#define PROF_SEC_BEGIN
+#define PROF_SEC(i)
+#define PROF_SEC_DONE
+#define PROF_DECL
+#define PROF_WAIT_BEGIN
+#define PROF_WAIT_END
+#define PROF_DONE(role)
+#endif
+
+__global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const RenderParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                     const int slot_bytes, const int front_bytes, const int window,
+                                                                     const int epi_bufs) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_slot_full[2], s_slot_empty[2], s_stage_full[UM_NP], s_stage_empty[UM_NP],
-        s_half_full[2], s_half_empty[2], s_rows[2];
+        s_half_full[2], s_half_empty[2], s_rows;
     __shared__ int2 s_chunk[UM_NP];   // (first column, columns) of the chunk in each stage
     __shared__ float s_emax[2][UM_EPI];
     __shared__ uint32_t s_tmem;
@@ -139,11 +215,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
     const int Wp = (W + 15) & ~15;  // columns of a full-width product
     const int n8 = um_n8(R);
 
-    // ---- shared memory: stages | epilogue staging | tap LUT (float, 4 shifted copies) | bf16 tap table (8 shifted
-    // copies, hi then lo) | front workspace | 2 slots --------------------------------------------------------------
+    // ---- shared memory: stages | epilogue tiles (1024-byte aligned) | tap LUT (float, 4 shifted copies) | bf16 tap
+    // table (8 shifted copies, hi then lo) | front workspace | 2 slots ---------------------------------------------
     unsigned char *stages = smem_raw;
     unsigned char *epi = stages + (size_t)UM_NP * UM_STAGE_BYTES;
-    float4 *lut = reinterpret_cast<float4 *>(epi + (size_t)UM_EPI * UM_EPI_BYTES);
+    float4 *lut = reinterpret_cast<float4 *>(epi + (size_t)UM_EPI * epi_bufs * UM_TILE_BYTES);
     unsigned char *btab = reinterpret_cast<unsigned char *>(lut) + lut_smem_bytes(p.n4);
     unsigned char *front_ws = btab + (size_t)2 * 8 * n8 * 16;
     unsigned char *slots = front_ws + front_bytes;
@@ -163,13 +239,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             s_norm = part;
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&s_slot_full[s], 1);
-                mbar_init(&s_slot_empty[s], 1 + UM_EPI + UM_NP);
+                mbar_init(&s_slot_empty[s], 1 + UM_EPI + 2 * UM_NP);
                 mbar_init(&s_half_full[s], 1);
                 mbar_init(&s_half_empty[s], UM_EPI);
-                mbar_init(&s_rows[s], 1);
             }
+            mbar_init(&s_rows, 1);
             for (int s = 0; s < UM_NP; ++s) {
-                mbar_init(&s_stage_full[s], 1);
+                mbar_init(&s_stage_full[s], 2);
                 mbar_init(&s_stage_empty[s], 1);
             }
             fence_mbar_init();
@@ -178,6 +254,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else if (warp == UM_EPI_WARP0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -201,41 +279,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
 
     if (warp == 0) {
         // =============================== front warp ==============================================================
+        PROF_DECL;
         unsigned char *base = front_ws;
-        double *stage_rows[2] = {nullptr, nullptr};
+        double *stage_rows = nullptr;  // one template's rows (xyz [cap][3] + intensity [cap]), refilled by cp.async.bulk
         if (p.stage) {
-            stage_rows[0] = reinterpret_cast<double *>(base);
-            stage_rows[1] = stage_rows[0] + p.cap * 4;
-            base += (size_t)2 * p.cap * 32;
+            stage_rows = reinterpret_cast<double *>(base);
+            base += (size_t)p.cap * 32;
         }
-        unsigned long long *hash = reinterpret_cast<unsigned long long *>(base);
-        base += (size_t)p.table_size * 8;
-        int *key = reinterpret_cast<int *>(base);
+        unsigned *pkey = reinterpret_cast<unsigned *>(base);  // [cap] column | row << 16 of spot j, ~0 = not in frame
         base += (size_t)p.cap * 4;
-        float *inten = reinterpret_cast<float *>(base);
+        float *pamp = reinterpret_cast<float *>(base);        // [cap]
         base += (size_t)p.cap * 4;
-        int *bins = reinterpret_cast<int *>(base);  // [W + 1] counting sort by column
-        auto prefetch = [&](int t, int buf) {
-            const uint32_t bx = (uint32_t)p.cap * 24u, bi = (uint32_t)p.cap * 8u;
-            mbar_expect_tx(&s_rows[buf], bx + bi);
-            bulk_g2s(stage_rows[buf], p.xyz + (size_t)t * p.cap * 3, bx, &s_rows[buf]);
-            bulk_g2s(stage_rows[buf] + p.cap * 3, p.intensity + (size_t)t * p.cap, bi, &s_rows[buf]);
+        int *bins = reinterpret_cast<int *>(base);            // [8 * 33] column histogram / offsets (W <= 256 columns + 1)
+        auto prefetch = [&](int t, int n) {  // the first n rows of template t (n rounded up to an even count: 16-byte units)
+            const uint32_t m = (uint32_t)min(p.cap, (n + 1) & ~1);
+            if (m == 0u) {
+                mbar_arrive(&s_rows);
+                return;
+            }
+            mbar_expect_tx(&s_rows, m * 32u);
+            bulk_g2s(stage_rows, p.xyz + (size_t)t * p.cap * 3, m * 24u, &s_rows);
+            bulk_g2s(stage_rows + p.cap * 3, p.intensity + (size_t)t * p.cap, m * 8u, &s_rows);
         };
+        // Templates come from the global ticket.  The atomic and the load of the template's spot count are global
+        // round trips of a microsecond behind a saturated store stream, so they run two templates ahead: (t0, n0) is
+        // the template in hand, (t1, n1) the next one (its rows are prefetched as soon as the staging buffer is
+        // free), t2 is drawn at the top of an iteration and only looked at at its end.
         auto draw = [&]() {
             int t = 0;
             if (lane == 0) t = atomicAdd(&p.ticket[0], 1);
-            return __shfl_sync(0xffffffffu, t, 0);
+            return t;  // (lane 0's value; broadcast where it is consumed)
         };
-        int t = draw();
-        int n_next = 0;
-        if (t < p.n_tmpl) {
-            n_next = p.count[t];
-            if (p.stage && lane == 0) prefetch(t, 0);
-        }
+        int t0 = __shfl_sync(0xffffffffu, draw(), 0), t1 = __shfl_sync(0xffffffffu, draw(), 0);
+        int n0 = t0 < p.n_tmpl ? p.count[t0] : 0, n1 = t1 < p.n_tmpl ? p.count[t1] : 0;
+        if (p.stage && lane == 0 && t0 < p.n_tmpl) prefetch(t0, n0);
         for (int k = 0;; ++k) {
-            const int slot = k & 1, buf = k & 1;
+            const int slot = k & 1;
+            const int t2_lane0 = draw();
+            PROF_WAIT_BEGIN;
             mbar_wait(&s_slot_empty[slot], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+            PROF_WAIT_END;
             UmHeader *hd = slot_header(slot);
+            const int t = t0;
             if (t >= p.n_tmpl) {  // out of work: stop slot
                 if (lane == 0) {
                     hd->t = -1;
@@ -243,111 +328,128 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                 }
                 break;
             }
-            const int n = min(n_next, p.cap);
-            const int t_next = draw();
-            if (t_next < p.n_tmpl) {
-                n_next = p.count[t_next];
-                if (p.stage && lane == 0) prefetch(t_next, buf ^ 1);
-            }
+            const int n = min(n0, p.cap);
             const double *sxyz = p.xyz + (size_t)t * p.cap * 3;
             const double *sint = p.intensity + (size_t)t * p.cap;
             if (p.stage) {
-                mbar_wait(&s_rows[buf], (uint32_t)(k >> 1) & 1u);
-                sxyz = stage_rows[buf];
-                sint = stage_rows[buf] + p.cap * 3;
+                PROF_WAIT_BEGIN;
+                mbar_wait(&s_rows, (uint32_t)k & 1u);
+                PROF_WAIT_END;
+                sxyz = stage_rows;
+                sint = stage_rows + p.cap * 3;
             }
             uint2 *spots = slot_spots(slot);
-
-            // ---- project, last-write-wins, compact (simulation2d.py:261-285, :422-430; detector_functions.py:297)
-            for (int e = lane; e < p.table_size; e += 32) hash[e] = 0ull;
-            for (int e = lane; e <= W; e += 32) bins[e] = 0;
-            __syncwarp();
-            for (int j = lane; j < n; j += 32) {
+            int n_live = 0;
+            auto project = [&](int j) -> unsigned {  // simulation2d.py:261-285, :422-430; astype(int) truncates
                 const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
                 const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
                 const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
-                int kk = -1;
-                if (px >= 0.0 && px < (double)W && py >= 0.0 && py < (double)H) {
-                    kk = (int)py * W + (int)px;
-                    const unsigned long long packed = ((unsigned long long)(kk + 1) << 32) | (unsigned)j;
-                    unsigned h = ((unsigned)kk * 2654435761u) & (p.table_size - 1);
-                    while (true) {
-                        unsigned long long cur = hash[h];
-                        if (cur == 0ull) {
-                            const unsigned long long old = atomicCAS(&hash[h], 0ull, packed);
-                            if (old == 0ull) break;
-                            cur = old;
-                        }
-                        if ((cur >> 32) == (unsigned long long)(kk + 1)) {
-                            atomicMax(&hash[h], packed);
-                            break;
-                        }
-                        h = (h + 1) & (p.table_size - 1);
+                if (px >= 0.0 && px < (double)W && py >= 0.0 && py < (double)H) return (unsigned)(int)px | ((unsigned)(int)py << 16);
+                return 0xffffffffu;
+            };
+            // The live spots are ordered by column (ties in list order): the order fixes the float32 sums
+            // (reproducible images), keeps the column windows of the chunks narrow, and of several spots in one pixel
+            // only the last in list order keeps its amplitude ("last write wins", detector_functions.py:297).
+            if (n <= 32) {
+                // ---- one spot per lane: rank and overwrite test by all-pairs shuffles, no shared-memory passes
+                unsigned kk = 0xffffffffu;
+                float a = 0.f;
+                if (lane < n) {
+                    kk = project(lane);
+                    a = (float)sint[lane];
+                }
+                __syncwarp();
+                if (p.stage && t1 < p.n_tmpl && lane == 0) prefetch(t1, n1);  // the rows have been consumed
+                const unsigned sk = kk == 0xffffffffu ? 0xffffffffu : (((kk & 0xffffu) << 5) | (unsigned)lane);
+                int rank = 0;
+                bool dead = false;
+                for (int i = 0; i < n; ++i) {
+                    const unsigned ski = __shfl_sync(0xffffffffu, sk, i), kki = __shfl_sync(0xffffffffu, kk, i);
+                    rank += ski < sk ? 1 : 0;
+                    dead |= (kki == kk) & (i > lane);
+                }
+                n_live = __popc(__ballot_sync(0xffffffffu, kk != 0xffffffffu));
+                if (kk != 0xffffffffu) spots[rank] = make_uint2(kk, dead ? 0u : __float_as_uint(a));
+            } else {
+                // ---- counting sort by column through shared memory
+                for (int e = lane; e < 8 * 33; e += 32) bins[e] = 0;
+                __syncwarp();
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    unsigned kk = 0xffffffffu;
+                    if (j < n) {
+                        kk = project(j);
+                        if (kk != 0xffffffffu) atomicAdd(&bins[(kk & 0xffffu) + 1], 1);
+                        pkey[j] = kk;
+                        pamp[j] = (float)sint[j];
                     }
+                    n_live += __popc(__ballot_sync(0xffffffffu, kk != 0xffffffffu));
                 }
-                key[j] = kk;
-                inten[j] = (float)sint[j];
-            }
-            __syncwarp();
-            // live spots in list order; with the column windows on, a stable counting sort by column decides their
-            // place (narrow windows per chunk of 16; stable = the float32 sums do not depend on scheduling)
-            int n_live = 0;
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                bool live = false;
-                int kk = -1;
-                if (j < n && (kk = key[j]) >= 0) {
-                    unsigned h = ((unsigned)kk * 2654435761u) & (p.table_size - 1);
-                    while ((hash[h] >> 32) != (unsigned long long)(kk + 1)) h = (h + 1) & (p.table_size - 1);
-                    live = (unsigned)(hash[h] & 0xffffffffu) == (unsigned)j;
-                }
-                if (j < n && !live) key[j] = -1;
-                if (live && window) atomicAdd(&bins[kk % W + 1], 1);
-                const unsigned mask = __ballot_sync(0xffffffffu, live);
-                if (live && !window) {
-                    const int d = n_live + __popc(mask & ((1u << lane) - 1u));
-                    spots[d] = make_uint2((unsigned)(kk % W) | ((unsigned)(kk / W) << 16), __float_as_uint(inten[j]));
-                }
-                n_live += __popc(mask);
-            }
-            __syncwarp();
-            if (window) {
-                // exclusive scan of the column histogram (bins[c + 1] = spots in column c) ...
-                int carry = 0;
-                for (int c0 = 0; c0 <= W; c0 += 32) {
-                    const int c = c0 + lane;
-                    int incl = c <= W ? bins[c] : 0;
+                __syncwarp();
+                if (p.stage && t1 < p.n_tmpl && lane == 0) prefetch(t1, n1);  // the rows have been consumed
+                // exclusive scan of bins[0 .. W]: each lane owns 9 consecutive entries (W + 1 <= 288)
+                {
+                    int loc[9], sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) {
+                        const int e = 9 * lane + i;
+                        loc[i] = e <= W ? bins[e] : 0;
+                        sum += loc[i];
+                    }
+                    int incl = sum;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int up = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += up;
                     }
-                    if (c <= W) bins[c] = carry + incl;  // = first slot of column c
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                    int run = incl - sum;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) {
+                        const int e = 9 * lane + i;
+                        run += loc[i];
+                        if (e <= W) bins[e] = run;  // inclusive over bins[0 .. e] = first slot of column e
+                    }
                 }
                 __syncwarp();
-                // ... then a stable scatter: 32 spots at a time, lanes of one column ranked by lane number
+                // stable scatter: 32 spots at a time, the lanes of one column ranked by lane number
                 for (int j0 = 0; j0 < n; j0 += 32) {
                     const int j = j0 + lane;
-                    const int kk = j < n ? key[j] : -1;
-                    const unsigned mask = __ballot_sync(0xffffffffu, kk >= 0);
-                    int col = 0, slot_at = 0;
+                    const unsigned kk = j < n ? pkey[j] : 0xffffffffu;
+                    const unsigned mask = __ballot_sync(0xffffffffu, kk != 0xffffffffu);
+                    int col = 0, at = 0;
                     unsigned peers = 0;
-                    if (kk >= 0) {
-                        col = kk % W;
+                    if (kk != 0xffffffffu) {
+                        col = (int)(kk & 0xffffu);
                         peers = __match_any_sync(mask, col);
-                        slot_at = bins[col] + __popc(peers & ((1u << lane) - 1u));
+                        at = bins[col] + __popc(peers & ((1u << lane) - 1u));
                     }
                     __syncwarp();
-                    if (kk >= 0) {
-                        spots[slot_at] = make_uint2((unsigned)col | ((unsigned)(kk / W) << 16), __float_as_uint(inten[j]));
-                        if ((peers & ((1u << lane) - 1u)) == 0u) bins[col] += __popc(peers);
+                    if (kk != 0xffffffffu) {
+                        spots[at] = make_uint2(kk, __float_as_uint(pamp[j]));
+                        if ((peers >> lane) == 1u) bins[col] = at + 1;  // the highest lane of the column leaves its end
                     }
                     __syncwarp();
                 }
+                // last write wins: a spot is overwritten if a later spot of its column (they follow it directly) sits in
+                // the same row
+                for (int i0 = 0; i0 < n_live; i0 += 32) {
+                    const int i = i0 + lane;
+                    if (i < n_live) {
+                        const unsigned kk = spots[i].x;
+                        for (int i2 = i + 1; i2 < n_live; ++i2) {
+                            const unsigned k2 = spots[i2].x;
+                            if ((k2 & 0xffffu) != (kk & 0xffffu)) break;
+                            if (k2 == kk) {
+                                spots[i].y = 0u;
+                                break;
+                            }
+                        }
+                    }
+                }
             }
+            __syncwarp();
             // ---- per-half lists: the spots whose box reaches rows [128 h, 128 h + 127] (the folded images of a
-            // spot lie inside its own clipped box)
+            // spot lie inside its own clipped box); overwritten spots are left out
             int n_half[2] = {0, 0};
             for (int h = 0; h < n_halves; ++h) {
                 unsigned short *list = slot_list(slot, h);
@@ -356,8 +458,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                     const int j = j0 + lane;
                     bool hit = false;
                     if (j < n_live) {
-                        const int sy = (int)(spots[j].x >> 16);
-                        hit = sy + R >= 128 * h && sy - R <= 128 * h + 127;
+                        const uint2 r = spots[j];
+                        const int sy = (int)(r.x >> 16);
+                        hit = r.y != 0u && sy + R >= 128 * h && sy - R <= 128 * h + 127;
                     }
                     const unsigned mask = __ballot_sync(0xffffffffu, hit);
                     if (hit) list[cnt + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)j;
@@ -373,25 +476,38 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_full[slot]);
-            t = t_next;
+            // rotate the look-ahead; only now are the ticket drawn at the top and its spot count needed
+            const int t2 = __shfl_sync(0xffffffffu, t2_lane0, 0);
+            t0 = t1;
+            n0 = n1;
+            t1 = t2;
+            n1 = t2 < p.n_tmpl ? p.count[t2] : 0;
         }
+        PROF_DONE(0);
     } else if (warp == 1) {
         // =============================== MMA issue ===============================================================
+        PROF_DECL;
         int c = 0;  // running chunk number: chunk c lives in stage c % UM_NP
         for (int k = 0;; ++k) {
             const int slot = k & 1;
+            PROF_WAIT_BEGIN;
             mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             if (hd->t < 0) break;
             for (int h = 0; h < n_halves; ++h) {
                 const int n_chunks = max(1, (hd->n_half[h] + 15) >> 4);
+                PROF_WAIT_BEGIN;
                 mbar_wait(&s_half_empty[h], ((uint32_t)k & 1u) ^ 1u);  // the epilogue has drained template k - 1
+                PROF_WAIT_END;
                 tc_fence_after();
                 for (int j = 0; j < n_chunks; ++j, ++c) {
                     const int s = c % UM_NP;
-                    mbar_wait(&s_stage_full[s], (uint32_t)(c / UM_NP) & 1u);
-                    tc_fence_after();
                     if (lane == 0) {
+                        PROF_WAIT_BEGIN;
+                        mbar_wait(&s_stage_full[s], (uint32_t)(c / UM_NP) & 1u);
+                        PROF_WAIT_END;
+                        tc_fence_after();
                         const int2 win = s_chunk[s];
                         const uint32_t st = smem_u32(stages) + (uint32_t)s * UM_STAGE_BYTES;
                         const uint64_t a_hi = umma_desc(st, 16 * 128, 128), a_lo = umma_desc(st + UM_A_BYTES, 16 * 128, 128);
@@ -410,101 +526,146 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             }
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
-    } else if (warp < 2 + UM_EPI) {
+        PROF_DONE(1);
+    } else if (warp >= UM_EPI_WARP0 && warp < UM_EPI_WARP0 + UM_EPI) {
         // =============================== epilogue ================================================================
-        const int q = warp & 3;  // tensor-memory lane quarter this warp may read
-        float *stg = reinterpret_cast<float *>(epi + (size_t)(warp - 2) * UM_EPI_BYTES);
-        const uint32_t stg_s = smem_u32(stg);
-        const int n_ct = (W + 31) >> 5;  // 32-column tiles
+        PROF_DECL;
+        PROF_SEC_DECL;
+        const int ew = warp - UM_EPI_WARP0;  // 0..7
+        const int q = warp & 3;              // tensor-memory lane quarter this warp may read
+        const int ch = ew >> 2;              // of the 32-column tiles of a half this warp takes ct = ch, ch + 2, ...
+        const uint32_t tile_s = smem_u32(epi + (size_t)ew * epi_bufs * UM_TILE_BYTES);
+        const int n_ct = (W + 31) >> 5;
+        const uint32_t tm_q = tm + ((uint32_t)(32 * q) << 16);
+        int nbuf = 0;  // staged tiles so far (buffer = nbuf & 1)
         for (int k = 0;; ++k) {
             const int slot = k & 1;
+            PROF_WAIT_BEGIN;
             mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             const int t = hd->t;
             if (t < 0) break;
             const bool norm = p.normalize && hd->n_live > 0;  // no spot in frame: zeros, returned un-normalised
             float scale = 1.f, vmax = INFINITY;
             if (norm) {
-                float m = -INFINITY;
+                // ---- pass 1: the template maximum, straight from the accumulators.  (Loops are kept rolled: the four
+                // roles of this kernel share the instruction cache.)
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
                 for (int h = 0; h < n_halves; ++h) {
+                    PROF_WAIT_BEGIN;
                     mbar_wait(&s_half_full[h], (uint32_t)k & 1u);
+                    PROF_WAIT_END;
                     tc_fence_after();
-                    const int row = 128 * h + 32 * q + lane;
-                    for (int ct = 0; ct < n_ct; ++ct) {
-                        float v[32];
-                        tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * 256 + 32 * ct), v);
-                        if (row < H) {
+                    if (128 * h + 32 * q >= H) continue;  // none of this warp's rows is in the image (warp-uniform)
+                    const bool row_ok = 128 * h + 32 * q + lane < H;
+                    uint32_t r[32];
+                    if (ch < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * ch), r);
+#pragma unroll 1
+                    for (int ct = ch; ct < n_ct; ct += 2) {
+                        PROF_SEC_BEGIN;
+                        tmem_wait(r);
+                        PROF_SEC(0);
+                        if (row_ok) {
                             if (32 * ct + 32 <= W) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+                                for (int j = 0; j < 32; j += 4) {
+                                    m0 = fmaxf(m0, __uint_as_float(r[j]));
+                                    m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+                                    m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+                                    m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+                                }
                             } else {
-#pragma unroll
+#pragma unroll  // (fully: a dynamic index would put the array in local memory)
                                 for (int j = 0; j < 32; ++j)
-                                    if (32 * ct + j < W) m = fmaxf(m, v[j]);
+                                    if (32 * ct + j < W) m0 = fmaxf(m0, __uint_as_float(r[j]));
                             }
                         }
+                        if (ct + 2 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 2)), r);
+                        PROF_SEC(1);
                     }
                 }
-                m = warp_max(m);
-                if (lane == 0) s_emax[k & 1][warp - 2] = m;
+                float m = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                if (lane == 0) s_emax[k & 1][ew] = m;
+                PROF_WAIT_BEGIN;
                 asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI * 32) : "memory");
+                PROF_WAIT_END;
 #pragma unroll
                 for (int e = 0; e < UM_EPI; ++e) m = fmaxf(m, s_emax[k & 1][e]);
                 vmax = m;
                 scale = 1.f / vmax;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
             }
-            float *img = p.images + (size_t)t * H * W;
+            // ---- pass 2: scale, stage, store
+#pragma unroll 1
             for (int h = 0; h < n_halves; ++h) {
                 if (!norm) {
+                    PROF_WAIT_BEGIN;
                     mbar_wait(&s_half_full[h], (uint32_t)k & 1u);
+                    PROF_WAIT_END;
                     tc_fence_after();
                 }
                 const int row0 = 128 * h + 32 * q;  // first image row of this warp's 32 lanes
-                for (int ct = 0; ct < n_ct; ++ct) {
-                    float v[32];
-                    tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * 256 + 32 * ct), v);
-                    if (ct == n_ct - 1) {  // last read of this half by this warp: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&s_half_empty[h]);
-                    }
-                    if (row0 >= H) continue;
-                    // numpy divides, so the maximum pixel is exactly 1: pin it (x * (1 / max) can be 1 ulp off)
+                if (row0 < H && ch < n_ct) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * ch), r);
+#pragma unroll 1
+                    for (int ct = ch; ct < n_ct; ct += 2) {
+                        PROF_SEC_BEGIN;
+                        tmem_wait(r);
+                        PROF_SEC(2);
+                        float v[32];
+                        // numpy divides, so the maximum pixel is exactly 1 while x * (1 / max) can be 1 ulp off: pin it
+                        // (vmax = +inf when the template is not normalised: never equal)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = (norm && v[j] == vmax) ? 1.0f : v[j] * scale;
-                    __syncwarp();  // the previous tile has been read out of the staging buffer
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + (uint32_t)(lane * UM_EPI_PITCH + 4 * j) * 4u),
-                                     "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                     : "memory");
-                    __syncwarp();
-                    // 4 rows x 128 contiguous bytes per store instruction
-                    const int cg = lane & 7, x = 32 * ct + 4 * cg;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + (lane >> 3), y = row0 + r;
-                        const float4 o = lds128v(stg_s + (uint32_t)(r * UM_EPI_PITCH + 4 * cg) * 4u);
-                        if (y < H && x < W) {
-                            float *d = img + (size_t)y * W + x;
-                            if (VEC) {
-                                __stcs(reinterpret_cast<float4 *>(d), o);
-                            } else {
-                                d[0] = o.x;
-                                if (x + 1 < W) d[1] = o.y;
-                                if (x + 2 < W) d[2] = o.z;
-                                if (x + 3 < W) d[3] = o.w;
-                            }
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(r[j]);
+                            v[j] = (x == vmax) ? 1.0f : x * scale;
                         }
+                        if (ct + 2 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 2)), r);
+                        PROF_SEC(3);
+                        // the copy that last read this buffer has finished reading it
+                        if (lane == 0) {
+                            if (epi_bufs == 2)
+                                tma_store_wait_read<1>();
+                            else
+                                tma_store_wait_read<0>();
+                        }
+                        __syncwarp();
+                        PROF_SEC(4);
+                        const uint32_t buf = tile_s + (uint32_t)(epi_bufs == 2 ? (nbuf & 1) : 0) * UM_TILE_BYTES;
+                        // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
+                                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                         : "memory");
+                        proxy_fence();
+                        __syncwarp();
+                        PROF_SEC(5);
+                        if (lane == 0) tma_store_tile(&tmap, buf, 32 * ct, row0, t);
+                        ++nbuf;
+                        PROF_SEC(6);
                     }
                 }
+                // this warp's reads of the half are complete: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_half_empty[h]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
+        if (lane == 0) tma_store_wait_read<0>();
+        if (ew == 0) {
+            PROF_DONE(2);
+            PROF_SEC_DONE;
+        }
     } else {
         // =============================== operand producers =======================================================
-        const int pw = warp - (2 + UM_EPI);  // producer index = its stage
+        PROF_DECL;
+        const int pi = warp < UM_EPI_WARP0 ? warp - 2 : warp - (UM_EPI_WARP0 + UM_EPI) + 2;  // 0..7
+        const int pw = pi >> 1, kh = pi & 1;  // team (= its stage), and the K group (spots 8 kh .. 8 kh + 7) this warp writes
         const uint32_t st = smem_u32(stages) + (uint32_t)pw * UM_STAGE_BYTES;
         const int k8 = lane & 7, gq = lane >> 3;
         LutRef L;
@@ -513,10 +674,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         L.last = p.n4 - 1;
         L.bias = R + LUT_PAD;
         const uint32_t bt_hi = smem_u32(btab), bt_lo = bt_hi + (uint32_t)(8 * n8 * 16);
+        const uint32_t a_hi = st + (uint32_t)(kh * (16 * 128) + k8 * 16), a_lo = a_hi + UM_A_BYTES;
+        const uint32_t b_hi = st + 2 * UM_A_BYTES + (uint32_t)(kh * (32 * 128) + k8 * 16), b_lo = b_hi + UM_B_BYTES;
         int c = 0;
         for (int k = 0;; ++k) {
             const int slot = k & 1;
+            PROF_WAIT_BEGIN;
             mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             if (hd->t < 0) break;
             const uint32_t spot_s = smem_u32(slot_spots(slot));
@@ -526,83 +691,96 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                 const uint32_t list_s = smem_u32(slot_list(slot, h));
                 for (int j = 0; j < n_chunks; ++j, ++c) {
                     if (c % UM_NP != pw) continue;
-                    // this lane's two spots of the chunk (K groups 0 and 1)
-                    int sx[2], sy[2];
-                    float amp[2];
-                    bool valid[2];
+                    // this lane's spot of the chunk; the column window needs the extent of all 16
+                    const int li = 16 * j + 8 * kh + k8, li_other = 16 * j + 8 * (kh ^ 1) + k8;
+                    const bool ok = li < n_h;
+                    int cx = 0, cy = 0;
+                    float am = 0.f;
                     int xmin = 1 << 20, xmax = -1;
-#pragma unroll
-                    for (int kh = 0; kh < 2; ++kh) {
-                        const int li = 16 * j + 8 * kh + k8;
-                        valid[kh] = li < n_h;
-                        sx[kh] = sy[kh] = 0;
-                        amp[kh] = 0.f;
-                        if (valid[kh]) {
-                            const uint2 r = lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li));
-                            sx[kh] = (int)(r.x & 0xffffu);
-                            sy[kh] = (int)(r.x >> 16);
-                            amp[kh] = __uint_as_float(r.y);
-                            xmin = min(xmin, sx[kh]);
-                            xmax = max(xmax, sx[kh]);
-                        }
+                    if (ok) {
+                        const uint2 r = lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li));
+                        cx = (int)(r.x & 0xffffu);
+                        cy = (int)(r.x >> 16);
+                        am = __uint_as_float(r.y);
+                        xmin = xmax = cx;
                     }
                     // column window of the chunk (the first chunk of a half covers every column: it zeroes them)
                     int col0 = 0, ncols = Wp;
                     if (window && j > 0) {
+                        if (li_other < n_h) {
+                            const int ox = (int)(lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li_other)).x & 0xffffu);
+                            xmin = min(xmin, ox);
+                            xmax = max(xmax, ox);
+                        }
                         xmin = -warp_max(-xmin);
                         xmax = warp_max(xmax);
                         col0 = max(0, xmin - R) & ~15;
                         ncols = ((min(W, xmax + R + 1) - col0) + 15) & ~15;
                     }
+                    PROF_WAIT_BEGIN;
                     mbar_wait(&s_stage_empty[pw], ((uint32_t)(c / UM_NP) & 1u) ^ 1u);
+                    PROF_WAIT_END;
+                    // ---- A: a_s Wy_s[y], rows 128 h + 8 g .. + 7.  scipy's mode="reflect" adds the mirror images of the
+                    // spot at -c - 1 (spots within R of the low border) and 2 n - 1 - c (high border); they only reach the
+                    // few groups next to that border, so most units are one table read
 #pragma unroll
-                    for (int kh = 0; kh < 2; ++kh) {
-                        // ---- A: a_s Wy_s[y], rows 128 h + 8 g .. + 7
-                        const uint32_t a_hi = st + (uint32_t)(kh * (16 * 128) + k8 * 16), a_lo = a_hi + UM_A_BYTES;
-                        const bool fold_y = sy[kh] < R || sy[kh] >= H - R;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int g = gq + 4 * i, y_lo = 128 * h + 8 * g;
-                            if (valid[kh] && y_lo + 7 >= sy[kh] - R && y_lo <= sy[kh] + R) {
-                                float4 w0, w1;
-                                if (fold_y) {
-                                    w0 = folded4s(L, y_lo + L.bias, sy[kh], H, R);
-                                    w1 = folded4s(L, y_lo + 4 + L.bias, sy[kh], H, R);
-                                } else {
-                                    const uint32_t a = fetch_addr(L, y_lo + L.bias - sy[kh]);
-                                    w0 = lds128(a);
-                                    w1 = lds128(a + 16u);
-                                }
-                                store_split8(a_hi + 128u * g, a_lo + 128u * g, w0, w1, amp[kh]);
-                            } else {
-                                sts128(a_hi + 128u * g, 0u, 0u, 0u, 0u);
-                                sts128(a_lo + 128u * g, 0u, 0u, 0u, 0u);
+                    for (int i = 0; i < 4; ++i) {
+                        const int g = gq + 4 * i, y_lo = 128 * h + 8 * g;
+                        if (ok && y_lo + 7 >= cy - R && y_lo <= cy + R) {
+                            const uint32_t a = fetch_addr(L, y_lo + L.bias - cy);
+                            float4 w0 = lds128(a), w1 = lds128(a + 16u);
+                            const int d_lo = y_lo + cy + 1, d_hi = y_lo + cy + 1 - 2 * H;
+                            if (d_lo <= R) {
+                                const uint32_t a2 = fetch_addr(L, d_lo + L.bias);
+                                w0 = add4(w0, lds128(a2));
+                                w1 = add4(w1, lds128(a2 + 16u));
                             }
-                        }
-                        // ---- B: Wx_s[x], columns col0 + 8 g .. + 7
-                        const uint32_t b_hi = st + 2 * UM_A_BYTES + (uint32_t)(kh * (32 * 128) + k8 * 16), b_lo = b_hi + UM_B_BYTES;
-                        const bool fold_x = sx[kh] < R || sx[kh] >= W - R;
-                        for (int g = gq; g < (ncols >> 3); g += 4) {
-                            const int x_lo = col0 + 8 * g;
-                            if (valid[kh] && x_lo + 7 >= sx[kh] - R && x_lo <= sx[kh] + R) {
-                                if (fold_x) {
-                                    const float4 w0 = folded4s(L, x_lo + L.bias, sx[kh], W, R);
-                                    const float4 w1 = folded4s(L, x_lo + 4 + L.bias, sx[kh], W, R);
-                                    store_split8(b_hi + 128u * g, b_lo + 128u * g, w0, w1, 1.0f);
-                                } else {  // interior: a shifted copy of the pre-split table
-                                    const int a = x_lo - sx[kh] + R + UM_BPAD;
-                                    const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
-                                    const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
-                                    sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
-                                    sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
-                                }
-                            } else {
-                                sts128(b_hi + 128u * g, 0u, 0u, 0u, 0u);
-                                sts128(b_lo + 128u * g, 0u, 0u, 0u, 0u);
+                            if (d_hi + 7 >= -R && d_hi <= R) {
+                                const uint32_t a3 = fetch_addr(L, d_hi + L.bias);
+                                w0 = add4(w0, lds128(a3));
+                                w1 = add4(w1, lds128(a3 + 16u));
                             }
+                            store_split8(a_hi + 128u * g, a_lo + 128u * g, w0, w1, am);
+                        } else {
+                            sts128(a_hi + 128u * g, 0u, 0u, 0u, 0u);
+                            sts128(a_lo + 128u * g, 0u, 0u, 0u, 0u);
                         }
                     }
-                    if (lane == 0) s_chunk[pw] = make_int2(col0, ncols);
+                    // ---- B: Wx_s[x], columns col0 + 8 g .. + 7: a shifted copy of the pre-split table, except for the
+                    // units a mirror image reaches
+#pragma unroll 2
+                    for (int g = gq; g < (ncols >> 3); g += 4) {
+                        const int x_lo = col0 + 8 * g;
+                        if (ok && x_lo + 7 >= cx - R && x_lo <= cx + R) {
+                            const int d_lo = x_lo + cx + 1, d_hi = x_lo + cx + 1 - 2 * W;
+                            const bool m_lo = d_lo <= R, m_hi = d_hi + 7 >= -R && d_hi <= R;
+                            if (m_lo || m_hi) {
+                                const uint32_t a1 = fetch_addr(L, x_lo + L.bias - cx);
+                                float4 w0 = lds128(a1), w1 = lds128(a1 + 16u);
+                                if (m_lo) {
+                                    const uint32_t a2 = fetch_addr(L, d_lo + L.bias);
+                                    w0 = add4(w0, lds128(a2));
+                                    w1 = add4(w1, lds128(a2 + 16u));
+                                }
+                                if (m_hi) {
+                                    const uint32_t a3 = fetch_addr(L, d_hi + L.bias);
+                                    w0 = add4(w0, lds128(a3));
+                                    w1 = add4(w1, lds128(a3 + 16u));
+                                }
+                                store_split8(b_hi + 128u * g, b_lo + 128u * g, w0, w1, 1.0f);
+                            } else {
+                                const int a = x_lo - cx + R + UM_BPAD;
+                                const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
+                                const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
+                                sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
+                                sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
+                            }
+                        } else {
+                            sts128(b_hi + 128u * g, 0u, 0u, 0u, 0u);
+                            sts128(b_lo + 128u * g, 0u, 0u, 0u, 0u);
+                        }
+                    }
+                    if (kh == 0 && lane == 0) s_chunk[pw] = make_int2(col0, ncols);
                     proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_stage_full[pw]);
@@ -611,32 +789,82 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
+        if (pi == 0) { PROF_DONE(3); }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(512) : "memory");
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart statically and has no
+// link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static std::atomic<void *> cached{nullptr};
+    void *fn = cached.load(std::memory_order_acquire);
+    if (fn == nullptr) {
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        cudaGetLastError();
+        cached.store(fn, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
 // Returns 1 if the tensor-core kernel was launched, 0 if the configuration is not eligible, < 0 on error.
 int launch_render_umma(RenderParams p, cudaStream_t st) {
-    if (p.H > 256 || p.W > 256 || p.cap > UM_MAX_CAP || p.radius >= p.W || p.radius >= p.H || p.radius > 120) return 0;
+    if (p.H > 256 || p.W > 256 || (p.W & 3) != 0 || p.cap > UM_MAX_CAP || p.radius >= p.W || p.radius >= p.H || p.radius > 120)
+        return 0;
+    EncodeTiledFn encode = encode_tiled();
+    if (encode == nullptr) return 0;
     const int n8 = um_n8(p.radius);
     const int slot_bytes = (32 + p.cap * 8 + 2 * p.cap * 2 + 15) & ~15;
-    if (p.cap > 256) p.stage = 0;  // large rows are read in place
-    const int front_bytes = (int)(((p.stage ? (size_t)2 * p.cap * 32 : 0) + (size_t)p.table_size * 8 + (size_t)p.cap * 8 +
-                                   (size_t)(p.W + 1 + 3) * 4 + 15) & ~(size_t)15);
-    const size_t smem = (size_t)UM_NP * UM_STAGE_BYTES + (size_t)UM_EPI * UM_EPI_BYTES + lut_smem_bytes(p.n4) +
-                        (size_t)2 * 8 * n8 * 16 + front_bytes + (size_t)2 * slot_bytes;
+    // spot rows are staged through shared memory whenever they are 16-byte granular (the front warp must not wait for
+    // global loads behind a saturated store stream)
+    p.stage = ((p.cap & 1) == 0 && (reinterpret_cast<uintptr_t>(p.xyz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.intensity) & 15) == 0 &&
+               option(OPT_RENDER_NOSTAGE) <= 0)
+                  ? 1
+                  : 0;
+    const int front_bytes = (int)(((p.stage ? (size_t)p.cap * 32 : 0) + (size_t)p.cap * 8 + (size_t)8 * 33 * 4 + 15) & ~(size_t)15);
+    // two staged tiles per epilogue warp when they fit (large capacities are tensor-pipe bound anyway)
+    int epi_bufs = 2;
+    auto smem_for = [&](int bufs) {
+        return (size_t)UM_NP * UM_STAGE_BYTES + (size_t)UM_EPI * bufs * UM_TILE_BYTES + lut_smem_bytes(p.n4) + (size_t)2 * 8 * n8 * 16 +
+               front_bytes + (size_t)2 * slot_bytes;
+    };
+    if (smem_for(2) > 226 * 1024) epi_bufs = 1;
+    const size_t smem = smem_for(epi_bufs);
     if (smem > 226 * 1024) return 0;  // (+ ~1 KB of static shared memory: barriers, alignment)
-    const bool vec = (p.W & 3) == 0;
-    void (*kern)(RenderParams, int, int, int) = vec ? render_umma_kernel<true> : render_umma_kernel<false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    // the image stack as a 3-D tensor (W, H, n_tmpl) of float32; a box is one 32 x 32 tile of one template
+    alignas(64) CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_tmpl};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4};
+    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.images, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("ds_render (tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        return -2;
+    }
+    cudaFuncSetAttribute(render_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const int window = option(OPT_RENDER_UMMA_WINDOW) == 0 ? 0 : 1;
     const int sms = num_sms();
     const int grid = p.n_tmpl < sms ? p.n_tmpl : sms;
-    kern<<<grid, UM_THREADS, smem, st>>>(p, slot_bytes, front_bytes, window);
+    render_umma_kernel<<<grid, UM_THREADS, smem, st>>>(p, tmap, slot_bytes, front_bytes, window, epi_bufs);
     const int rc = check_launch("ds_render (tcgen05)");
     return rc == 0 ? 1 : rc;
 }
 
 }  // namespace ds
+
+#ifdef DS_PROF
+extern "C" int ds_debug_umma_prof(unsigned long long *out_host /*[16]*/) {
+    if (cudaMemcpyFromSymbol(out_host, ds::g_um_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    return cudaMemcpyFromSymbol(out_host + 8, ds::g_um_prof2, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
