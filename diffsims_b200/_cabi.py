@@ -15,7 +15,7 @@ _lib = None
 
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors", "ds_pack_gtable",
-           "ds_simulate", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
+           "ds_simulate", "ds_render_scratch_bytes", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
            "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points")
 ABI_VERSION = 2
 
@@ -55,6 +55,8 @@ def lib():
     L.ds_get_option.argtypes = [c_char_p, P]
     for s in SYMBOLS[2:]:
         getattr(L, s).restype = c_int32
+    L.ds_render_scratch_bytes.argtypes = [I, I]
+    L.ds_render_scratch_bytes.restype = ctypes.c_int64
     L.ds_beam_grid_num_blocks.restype = ctypes.c_int64
     L.ds_beam_points_num_blocks.restype = ctypes.c_int64
     _lib = L

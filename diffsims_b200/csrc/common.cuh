@@ -92,13 +92,27 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase) {
         : "memory");                                       // polling (polls would compete with the working warps' LDS / STS)
     return ok != 0;
 }
-// Waits are bounded: a barrier that does not complete within ~10^10 cycles (seconds) is a protocol bug, and the
-// kernel traps (the launch fails loudly with a sticky error) instead of hanging the device.
+// Waits are bounded: a barrier that does not complete within ~2^28 polls (each poll suspends in hardware up to the
+// hint, so this is many seconds) is a protocol bug, and the kernel traps -- the launch fails loudly with a sticky
+// error instead of hanging the device.  The bound is a poll counter, not a clock read: idle roles of the
+// warp-specialised kernels sit in this loop and every instruction in it competes with the working warps.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    if (mbar_try(bar, phase)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try(bar, phase))
-        if (clock64() - t0 > 10000000000ll) __trap();
+        if (++polls > (1u << 28)) __trap();
+}
+// one elected lane of a converged warp (elect.sync): the compiler treats the predicate as warp-uniform, so uniform-
+// datapath instructions (tcgen05.mma, cp.async.bulk.tensor, ...) issue without a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -23,7 +23,7 @@
 namespace ds {
 
 int launch_render_pipelined(RenderParams p, cudaStream_t st);
-int launch_render_umma(RenderParams p, cudaStream_t st);
+int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st);
 
 // A "group" of G warps (G = 1, 2, 4 or 8) owns one template at a time; a CTA holds 8 / G groups and is
 // persistent (templates are drawn from a global ticket).  G = 1 keeps 8 independent templates in flight per
@@ -381,10 +381,15 @@ static int launch_render(const RenderParams &p, int group_bytes, size_t lut_byte
 
 }  // namespace ds
 
+extern "C" int64_t ds_render_scratch_bytes(int32_t n_tmpl, int32_t cap) {
+    if (n_tmpl < 0 || cap < 0) return -1;
+    return 16 + (int64_t)n_tmpl * ds::umma_record_bytes(cap);
+}
+
 extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const double *xyz,
                          const double *intensity, int32_t H, int32_t W, double calibration, double cx, double cy,
                          double in_plane_angle_deg, int32_t mirrored, int32_t fast, double sigma, int32_t radius,
-                         double clip_threshold, int32_t normalize, float *images, int32_t *ticket,
+                         double clip_threshold, int32_t normalize, float *images, void *scratch,
                          double mean_spots_hint) {
     using namespace ds;
     DS_REQUIRE(n_tmpl >= 0 && cap > 0 && H > 0 && W > 0, "ds_render: bad sizes");
@@ -392,7 +397,9 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     DS_REQUIRE(calibration != 0.0, "ds_render: calibration cannot be zero");
     DS_REQUIRE(sigma > 0.0, "ds_render: sigma must be positive");
     DS_REQUIRE((reinterpret_cast<uintptr_t>(images) & 15) == 0, "ds_render: images must be 16-byte aligned");
-    DS_REQUIRE(ticket != nullptr || n_tmpl == 0, "ds_render: the ticket scratch words are required");
+    DS_REQUIRE(scratch != nullptr || n_tmpl == 0, "ds_render: the scratch buffer is required");
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "ds_render: scratch must be 16-byte aligned");
+    int32_t *ticket = static_cast<int32_t *>(scratch);  // [0..1]: dynamic template hand-out; records from byte 16 on
     if (n_tmpl == 0) return 0;
     RenderParams p;
     p.n_tmpl = n_tmpl;
@@ -474,12 +481,13 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     // The ticket words start every launch at zero (a launch that died mid-way cannot poison the next one).
     cudaMemsetAsync(ticket, 0, 2 * sizeof(int32_t), st);
     // Templates of up to 256 x 256 px with more than a handful of reflections: the tcgen05 kernel (render_umma.cu);
-    // option render_umma = 0 / 1 forces it off / on.  Measured cross-over on B200: see DESIGN.md.
+    // option render_umma = 0 / 1 forces it off / on.  Measured cross-over on B200 (profiles/r02_k3_variants*.txt): the
+    // float32 pipelined kernel wins below ~16 reflections per template (sigma 10), the tcgen05 kernel above.
     if (fast && !wide && !g_forced) {
         const int um = option(OPT_RENDER_UMMA);
-        const bool want_umma = um >= 0 ? um != 0 : (cap > 32 || mean_spots_hint >= 12.0);
+        const bool want_umma = um >= 0 ? um != 0 : (mean_spots_hint > 0.0 ? mean_spots_hint >= 16.0 : cap >= 96);
         if (want_umma) {
-            const int rc = launch_render_umma(p, st);
+            const int rc = launch_render_umma(p, static_cast<unsigned char *>(scratch) + 16, st);
             if (rc != 0) return rc < 0 ? rc : 0;
         }
     }

@@ -10,6 +10,10 @@
 namespace ds {
 
 int num_sms();
+// bytes of one prepared-template record of the tcgen05 render path (render_prep.cu, render_umma.cu)
+//   int32 t, n_live, n_half[2], pad[4] | uint2 spot[cap] | uint16 list[2][cap] | uint32 window[2][ceil(cap / 16)]
+__host__ __device__ inline int umma_windows_offset(int cap) { return 32 + cap * 8 + 2 * cap * 2; }
+__host__ __device__ inline int umma_record_bytes(int cap) { return (umma_windows_offset(cap) + 2 * ((cap + 15) / 16) * 4 + 15) & ~15; }
 
 constexpr int RN_WARPS = 8;
 constexpr int RN_THREADS = RN_WARPS * 32;

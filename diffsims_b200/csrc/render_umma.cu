@@ -19,12 +19,12 @@
 //     also clips partial tiles), double-buffered so that tensor-memory reads, stores and copies overlap.
 //
 // Warp roles of the persistent CTA (one per SM, templates drawn from the global ticket):
-//   warp 0        front: prefetched spot rows -> float64 projection -> counting sort by column (ties in list
-//                 order) -> last-write-wins inside a pixel -> per-half lists -> publishes one of two template slots
+//   warp 0        front: draws templates from the ticket and fetches their prepared records (render_prep.cu: live
+//                 spots sorted by column, per-half lists) into one of four shared-memory slots with cp.async.bulk
 //   warp 1        MMA issue (lane 0), owns the tensor-memory allocation (512 columns = 2 halves x 256)
 //   warps 4..11   epilogue (tensor-memory lane quarter = warp % 4; two warps per quarter share its column tiles)
 //   warps 2, 3, 12..15   operand producers: three teams of two warps, one shared-memory stage per team
-// mbarriers: slot full/empty (front <-> everyone), stage full/empty (producer <-> tcgen05.commit),
+// mbarriers: slot full (bulk copy -> everyone) / empty (everyone -> front), stage full/empty (producer <-> tcgen05.commit),
 // half full/empty (tcgen05.commit <-> epilogue).  Bound: tensor pipe for dense templates, HBM write otherwise.
 //
 // Reference: diffsims/pattern/detector_functions.py:293-300 (assignment + scipy.ndimage.gaussian_filter),
@@ -49,10 +49,12 @@ constexpr int UM_STAGE_BYTES = 2 * UM_A_BYTES + 2 * UM_B_BYTES;  // 24 KB
 constexpr int UM_TILE_BYTES = 32 * 32 * 4;     // one staged 32 x 32 float tile (128-byte rows, 128B swizzle)
 constexpr int UM_BPAD = 8;                     // zero padding of the bf16 tap table on either side
 constexpr int UM_MAX_CAP = 1024;
+constexpr int UM_SLOTS = 4;                    // template records in flight per CTA
 
-struct UmHeader {  // 32 bytes at the start of a slot
+struct UmHeader {  // 32 bytes at the start of a record / slot (written by render_prepare_kernel)
     int t, n_live, n_half[2], pad[4];
 };
+
 
 // entries (16 bytes = 8 taps) per shifted copy of the bf16 tap table
 __host__ __device__ inline int um_n8(int radius) { return (2 * radius + 2 * UM_BPAD + 1 + 7) / 8 + 1; }
@@ -107,6 +109,11 @@ __device__ __forceinline__ float4 lds128v(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds32v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint2 lds64v(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
@@ -127,6 +134,49 @@ __device__ __forceinline__ void store_split8(uint32_t hi_addr, uint32_t lo_addr,
     bf16_split2(a * w1.z, a * w1.w, h[3], l[3]);
     sts128(hi_addr, h[0], h[1], h[2], h[3]);
     sts128(lo_addr, l[0], l[1], l[2], l[3]);
+}
+
+
+// One lane's share of a chunk's A operand: four 16-byte units  a_s Wy_s[y]  for the rows 128 h + 8 (gq + 4 i) .. + 7.
+// Straight-line code (the four units overlap): a unit the spot does not reach reads the all-zero head of the tap
+// table.  scipy's mode="reflect" adds the mirror images of the spot at -c - 1 (reaches rows < R; LO halves) and at
+// 2 H - 1 - c (rows >= H - R; HI halves), one more table read per unit where the half touches that border.
+template <bool LO, bool HI>
+__device__ __forceinline__ void produce_a(const LutRef &L, uint32_t a_hi, uint32_t a_lo, int gq, int row_base, bool ok, int cy,
+                                          float am, int R, int H) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int g = gq + 4 * i, y_lo = row_base + 8 * g;
+        const bool hit = ok && y_lo + 7 >= cy - R && y_lo <= cy + R;
+        const uint32_t a = fetch_addr(L, hit ? y_lo + L.bias - cy : 0);
+        float4 w0 = lds128(a), w1 = lds128(a + 16u);
+        if (LO) {
+            const int d = y_lo + cy + 1;
+            const uint32_t a2 = fetch_addr(L, (hit && d <= R) ? d + L.bias : 0);
+            w0 = add4(w0, lds128(a2));
+            w1 = add4(w1, lds128(a2 + 16u));
+        }
+        if (HI) {
+            const int d = y_lo + cy + 1 - 2 * H;
+            const uint32_t a3 = fetch_addr(L, (hit && d + 7 >= -R && d <= R) ? d + L.bias : 0);
+            w0 = add4(w0, lds128(a3));
+            w1 = add4(w1, lds128(a3 + 16u));
+        }
+        store_split8(a_hi + 128u * g, a_lo + 128u * g, w0, w1, am);
+    }
+}
+// One unit of the B operand in float32 (columns next to a border: direct taps plus the mirror images), then split.
+__device__ __forceinline__ void produce_b_border(const LutRef &L, uint32_t hi_addr, uint32_t lo_addr, int x_lo, bool ok, int cx, int R,
+                                                 int W) {
+    const bool hit = ok && x_lo + 7 >= cx - R && x_lo <= cx + R;
+    const uint32_t a1 = fetch_addr(L, hit ? x_lo + L.bias - cx : 0);
+    float4 w0 = lds128(a1), w1 = lds128(a1 + 16u);
+    const int d2 = x_lo + cx + 1, d3 = x_lo + cx + 1 - 2 * W;
+    const uint32_t a2 = fetch_addr(L, (hit && d2 <= R) ? d2 + L.bias : 0);
+    const uint32_t a3 = fetch_addr(L, (hit && d3 + 7 >= -R && d3 <= R) ? d3 + L.bias : 0);
+    w0 = add4(add4(w0, lds128(a2)), lds128(a3));
+    w1 = add4(add4(w1, lds128(a2 + 16u)), lds128(a3 + 16u));
+    store_split8(hi_addr, lo_addr, w0, w1, 1.0f);
 }
 
 // tcgen05.ld without the wait (the registers are only valid after tmem_wait on the same array)
@@ -177,9 +227,9 @@ __device__ unsigned long long g_um_prof2[8];  // first epilogue warp of CTA 0: c
         prof_sec[i] += now_ - prof_s0;     \
         prof_s0 = now_;                    \
     }
-#define PROF_SEC_DONE                                                                 \
-    if (blockIdx.x == 0 && lane == 0)                                                 \
-        for (int i_ = 0; i_ < 8; ++i_) g_um_prof2[i_] = (unsigned long long)prof_sec[i_];
+#define PROF_SEC_STORE(first, count)                                                 \
+    if (blockIdx.x == 0 && lane == 0)                                                \
+        for (int i_ = first; i_ < first + count; ++i_) g_um_prof2[i_] = (unsigned long long)prof_sec[i_];
 #define PROF_DECL long long prof_t0 = clock64(), prof_wait = 0, prof_w0 = 0
 #define PROF_WAIT_BEGIN prof_w0 = clock64()
 #define PROF_WAIT_END prof_wait += clock64() - prof_w0
@@ -192,7 +242,7 @@ __device__ unsigned long long g_um_prof2[8];  // first epilogue warp of CTA 0: c
 #define PROF_SEC_DECL
 #define PROF_SEC_BEGIN
 #define PROF_SEC(i)
-#define PROF_SEC_DONE
+#define PROF_SEC_STORE(first, count)
 #define PROF_DECL
 #define PROF_WAIT_BEGIN
 #define PROF_WAIT_END
@@ -200,12 +250,11 @@ __device__ unsigned long long g_um_prof2[8];  // first epilogue warp of CTA 0: c
 #endif
 
 __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const RenderParams p, const __grid_constant__ CUtensorMap tmap,
-                                                                     const int slot_bytes, const int front_bytes, const int window,
-                                                                     const int epi_bufs) {
+                                                                     const unsigned char *records, const int slot_bytes,
+                                                                     const int window, const int epi_bufs) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_slot_full[2], s_slot_empty[2], s_stage_full[UM_NP], s_stage_empty[UM_NP],
-        s_half_full[2], s_half_empty[2], s_rows;
-    __shared__ int2 s_chunk[UM_NP];   // (first column, columns) of the chunk in each stage
+    __shared__ __align__(8) uint64_t s_slot_full[UM_SLOTS], s_slot_empty[UM_SLOTS], s_stage_full[UM_NP], s_stage_empty[UM_NP],
+        s_half_full[2], s_half_empty[2];
     __shared__ float s_emax[2][UM_EPI];
     __shared__ uint32_t s_tmem;
     __shared__ double s_norm;
@@ -216,13 +265,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
     const int n8 = um_n8(R);
 
     // ---- shared memory: stages | epilogue tiles (1024-byte aligned) | tap LUT (float, 4 shifted copies) | bf16 tap
-    // table (8 shifted copies, hi then lo) | front workspace | 2 slots ---------------------------------------------
+    // table (8 shifted copies, hi then lo) | 4 slots ---------------------------------------------------------------
     unsigned char *stages = smem_raw;
     unsigned char *epi = stages + (size_t)UM_NP * UM_STAGE_BYTES;
     float4 *lut = reinterpret_cast<float4 *>(epi + (size_t)UM_EPI * epi_bufs * UM_TILE_BYTES);
     unsigned char *btab = reinterpret_cast<unsigned char *>(lut) + lut_smem_bytes(p.n4);
-    unsigned char *front_ws = btab + (size_t)2 * 8 * n8 * 16;
-    unsigned char *slots = front_ws + front_bytes;
+    unsigned char *slots = btab + (size_t)2 * 8 * n8 * 16;
     auto slot_header = [&](int s) { return reinterpret_cast<UmHeader *>(slots + (size_t)s * slot_bytes); };
     auto slot_spots = [&](int s) { return reinterpret_cast<uint2 *>(slots + (size_t)s * slot_bytes + 32); };
     auto slot_list = [&](int s, int h) {
@@ -237,13 +285,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) {
             s_norm = part;
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < UM_SLOTS; ++s) {
                 mbar_init(&s_slot_full[s], 1);
                 mbar_init(&s_slot_empty[s], 1 + UM_EPI + 2 * UM_NP);
+            }
+            for (int s = 0; s < 2; ++s) {
                 mbar_init(&s_half_full[s], 1);
                 mbar_init(&s_half_empty[s], UM_EPI);
             }
-            mbar_init(&s_rows, 1);
             for (int s = 0; s < UM_NP; ++s) {
                 mbar_init(&s_stage_full[s], 2);
                 mbar_init(&s_stage_empty[s], 1);
@@ -280,257 +329,91 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
     if (warp == 0) {
         // =============================== front warp ==============================================================
         PROF_DECL;
-        unsigned char *base = front_ws;
-        double *stage_rows = nullptr;  // one template's rows (xyz [cap][3] + intensity [cap]), refilled by cp.async.bulk
-        if (p.stage) {
-            stage_rows = reinterpret_cast<double *>(base);
-            base += (size_t)p.cap * 32;
-        }
-        unsigned *pkey = reinterpret_cast<unsigned *>(base);  // [cap] column | row << 16 of spot j, ~0 = not in frame
-        base += (size_t)p.cap * 4;
-        float *pamp = reinterpret_cast<float *>(base);        // [cap]
-        base += (size_t)p.cap * 4;
-        int *bins = reinterpret_cast<int *>(base);            // [8 * 33] column histogram / offsets (W <= 256 columns + 1)
-        auto prefetch = [&](int t, int n) {  // the first n rows of template t (n rounded up to an even count: 16-byte units)
-            const uint32_t m = (uint32_t)min(p.cap, (n + 1) & ~1);
-            if (m == 0u) {
-                mbar_arrive(&s_rows);
-                return;
-            }
-            mbar_expect_tx(&s_rows, m * 32u);
-            bulk_g2s(stage_rows, p.xyz + (size_t)t * p.cap * 3, m * 24u, &s_rows);
-            bulk_g2s(stage_rows + p.cap * 3, p.intensity + (size_t)t * p.cap, m * 8u, &s_rows);
-        };
-        // Templates come from the global ticket.  The atomic and the load of the template's spot count are global
-        // round trips of a microsecond behind a saturated store stream, so they run two templates ahead: (t0, n0) is
-        // the template in hand, (t1, n1) the next one (its rows are prefetched as soon as the staging buffer is
-        // free), t2 is drawn at the top of an iteration and only looked at at its end.
-        auto draw = [&]() {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&p.ticket[0], 1);
-            return t;  // (lane 0's value; broadcast where it is consumed)
-        };
-        int t0 = __shfl_sync(0xffffffffu, draw(), 0), t1 = __shfl_sync(0xffffffffu, draw(), 0);
-        int n0 = t0 < p.n_tmpl ? p.count[t0] : 0, n1 = t1 < p.n_tmpl ? p.count[t1] : 0;
-        if (p.stage && lane == 0 && t0 < p.n_tmpl) prefetch(t0, n0);
+        // The ticket atomic is a global round trip of a microsecond behind a saturated store stream, so it runs one
+        // template ahead of the record fetch (which is itself up to UM_SLOTS templates ahead of the consumers).
+        int t_ahead = 0;
+        if (lane == 0) t_ahead = atomicAdd(&p.ticket[0], 1);
         for (int k = 0;; ++k) {
-            const int slot = k & 1;
-            const int t2_lane0 = draw();
+            const int slot = k % UM_SLOTS;
+            const int t = __shfl_sync(0xffffffffu, t_ahead, 0);
+            if (lane == 0 && t < p.n_tmpl) t_ahead = atomicAdd(&p.ticket[0], 1);
             PROF_WAIT_BEGIN;
-            mbar_wait(&s_slot_empty[slot], ((uint32_t)(k >> 1) & 1u) ^ 1u);
+            mbar_wait(&s_slot_empty[slot], ((uint32_t)(k / UM_SLOTS) & 1u) ^ 1u);
             PROF_WAIT_END;
-            UmHeader *hd = slot_header(slot);
-            const int t = t0;
             if (t >= p.n_tmpl) {  // out of work: stop slot
                 if (lane == 0) {
-                    hd->t = -1;
+                    slot_header(slot)->t = -1;
                     mbar_arrive(&s_slot_full[slot]);
                 }
                 break;
             }
-            const int n = min(n0, p.cap);
-            const double *sxyz = p.xyz + (size_t)t * p.cap * 3;
-            const double *sint = p.intensity + (size_t)t * p.cap;
-            if (p.stage) {
-                PROF_WAIT_BEGIN;
-                mbar_wait(&s_rows, (uint32_t)k & 1u);
-                PROF_WAIT_END;
-                sxyz = stage_rows;
-                sint = stage_rows + p.cap * 3;
-            }
-            uint2 *spots = slot_spots(slot);
-            int n_live = 0;
-            auto project = [&](int j) -> unsigned {  // simulation2d.py:261-285, :422-430; astype(int) truncates
-                const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
-                const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-                const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
-                if (px >= 0.0 && px < (double)W && py >= 0.0 && py < (double)H) return (unsigned)(int)px | ((unsigned)(int)py << 16);
-                return 0xffffffffu;
-            };
-            // The live spots are ordered by column (ties in list order): the order fixes the float32 sums
-            // (reproducible images), keeps the column windows of the chunks narrow, and of several spots in one pixel
-            // only the last in list order keeps its amplitude ("last write wins", detector_functions.py:297).
-            if (n <= 32) {
-                // ---- one spot per lane: rank and overwrite test by all-pairs shuffles, no shared-memory passes
-                unsigned kk = 0xffffffffu;
-                float a = 0.f;
-                if (lane < n) {
-                    kk = project(lane);
-                    a = (float)sint[lane];
-                }
-                __syncwarp();
-                if (p.stage && t1 < p.n_tmpl && lane == 0) prefetch(t1, n1);  // the rows have been consumed
-                const unsigned sk = kk == 0xffffffffu ? 0xffffffffu : (((kk & 0xffffu) << 5) | (unsigned)lane);
-                int rank = 0;
-                bool dead = false;
-                for (int i = 0; i < n; ++i) {
-                    const unsigned ski = __shfl_sync(0xffffffffu, sk, i), kki = __shfl_sync(0xffffffffu, kk, i);
-                    rank += ski < sk ? 1 : 0;
-                    dead |= (kki == kk) & (i > lane);
-                }
-                n_live = __popc(__ballot_sync(0xffffffffu, kk != 0xffffffffu));
-                if (kk != 0xffffffffu) spots[rank] = make_uint2(kk, dead ? 0u : __float_as_uint(a));
-            } else {
-                // ---- counting sort by column through shared memory
-                for (int e = lane; e < 8 * 33; e += 32) bins[e] = 0;
-                __syncwarp();
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    unsigned kk = 0xffffffffu;
-                    if (j < n) {
-                        kk = project(j);
-                        if (kk != 0xffffffffu) atomicAdd(&bins[(kk & 0xffffu) + 1], 1);
-                        pkey[j] = kk;
-                        pamp[j] = (float)sint[j];
-                    }
-                    n_live += __popc(__ballot_sync(0xffffffffu, kk != 0xffffffffu));
-                }
-                __syncwarp();
-                if (p.stage && t1 < p.n_tmpl && lane == 0) prefetch(t1, n1);  // the rows have been consumed
-                // exclusive scan of bins[0 .. W]: each lane owns 9 consecutive entries (W + 1 <= 288)
-                {
-                    int loc[9], sum = 0;
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) {
-                        const int e = 9 * lane + i;
-                        loc[i] = e <= W ? bins[e] : 0;
-                        sum += loc[i];
-                    }
-                    int incl = sum;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    int run = incl - sum;
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) {
-                        const int e = 9 * lane + i;
-                        run += loc[i];
-                        if (e <= W) bins[e] = run;  // inclusive over bins[0 .. e] = first slot of column e
-                    }
-                }
-                __syncwarp();
-                // stable scatter: 32 spots at a time, the lanes of one column ranked by lane number
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    const unsigned kk = j < n ? pkey[j] : 0xffffffffu;
-                    const unsigned mask = __ballot_sync(0xffffffffu, kk != 0xffffffffu);
-                    int col = 0, at = 0;
-                    unsigned peers = 0;
-                    if (kk != 0xffffffffu) {
-                        col = (int)(kk & 0xffffu);
-                        peers = __match_any_sync(mask, col);
-                        at = bins[col] + __popc(peers & ((1u << lane) - 1u));
-                    }
-                    __syncwarp();
-                    if (kk != 0xffffffffu) {
-                        spots[at] = make_uint2(kk, __float_as_uint(pamp[j]));
-                        if ((peers >> lane) == 1u) bins[col] = at + 1;  // the highest lane of the column leaves its end
-                    }
-                    __syncwarp();
-                }
-                // last write wins: a spot is overwritten if a later spot of its column (they follow it directly) sits in
-                // the same row
-                for (int i0 = 0; i0 < n_live; i0 += 32) {
-                    const int i = i0 + lane;
-                    if (i < n_live) {
-                        const unsigned kk = spots[i].x;
-                        for (int i2 = i + 1; i2 < n_live; ++i2) {
-                            const unsigned k2 = spots[i2].x;
-                            if ((k2 & 0xffffu) != (kk & 0xffffu)) break;
-                            if (k2 == kk) {
-                                spots[i].y = 0u;
-                                break;
-                            }
-                        }
-                    }
-                }
+            if (lane == 0) {  // the copy's completion is the slot's `full` signal
+                mbar_expect_tx(&s_slot_full[slot], (uint32_t)slot_bytes);
+                bulk_g2s(slots + (size_t)slot * slot_bytes, records + (size_t)t * slot_bytes, (uint32_t)slot_bytes, &s_slot_full[slot]);
             }
             __syncwarp();
-            // ---- per-half lists: the spots whose box reaches rows [128 h, 128 h + 127] (the folded images of a
-            // spot lie inside its own clipped box); overwritten spots are left out
-            int n_half[2] = {0, 0};
-            for (int h = 0; h < n_halves; ++h) {
-                unsigned short *list = slot_list(slot, h);
-                int cnt = 0;
-                for (int j0 = 0; j0 < n_live; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool hit = false;
-                    if (j < n_live) {
-                        const uint2 r = spots[j];
-                        const int sy = (int)(r.x >> 16);
-                        hit = r.y != 0u && sy + R >= 128 * h && sy - R <= 128 * h + 127;
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                    if (hit) list[cnt + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)j;
-                    cnt += __popc(mask);
-                }
-                n_half[h] = cnt;
-            }
-            if (lane == 0) {
-                hd->t = t;
-                hd->n_live = n_live;
-                hd->n_half[0] = n_half[0];
-                hd->n_half[1] = n_half[1];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_slot_full[slot]);
-            // rotate the look-ahead; only now are the ticket drawn at the top and its spot count needed
-            const int t2 = __shfl_sync(0xffffffffu, t2_lane0, 0);
-            t0 = t1;
-            n0 = n1;
-            t1 = t2;
-            n1 = t2 < p.n_tmpl ? p.count[t2] : 0;
         }
         PROF_DONE(0);
     } else if (warp == 1) {
         // =============================== MMA issue ===============================================================
         PROF_DECL;
-        int c = 0;  // running chunk number: chunk c lives in stage c % UM_NP
+        PROF_SEC_DECL;
+        int stage = 0;           // chunks go round the UM_NP stages; `sphase` is the parity of a stage's current fill
+        uint32_t sphase = 0;
+        const uint32_t st0 = smem_u32(stages);
+        // shared-memory descriptors of stage 0; a stage further on adds its byte offset >> 4 to the address field
+        const uint64_t d_a_hi = umma_desc(st0, 16 * 128, 128), d_a_lo = umma_desc(st0 + UM_A_BYTES, 16 * 128, 128);
+        const uint64_t d_b_hi = umma_desc(st0 + 2 * UM_A_BYTES, 32 * 128, 128);
+        const uint64_t d_b_lo = umma_desc(st0 + 2 * UM_A_BYTES + UM_B_BYTES, 32 * 128, 128);
         for (int k = 0;; ++k) {
-            const int slot = k & 1;
+            const int slot = k % UM_SLOTS;
             PROF_WAIT_BEGIN;
-            mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            mbar_wait(&s_slot_full[slot], (uint32_t)(k / UM_SLOTS) & 1u);
             PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             if (hd->t < 0) break;
+            const uint32_t *wins = reinterpret_cast<const uint32_t *>(slots + (size_t)slot * slot_bytes + umma_windows_offset(p.cap));
             for (int h = 0; h < n_halves; ++h) {
                 const int n_chunks = max(1, (hd->n_half[h] + 15) >> 4);
                 PROF_WAIT_BEGIN;
                 mbar_wait(&s_half_empty[h], ((uint32_t)k & 1u) ^ 1u);  // the epilogue has drained template k - 1
                 PROF_WAIT_END;
                 tc_fence_after();
-                for (int j = 0; j < n_chunks; ++j, ++c) {
-                    const int s = c % UM_NP;
-                    if (lane == 0) {
+                if (elect_one()) {
+                    const uint32_t *win_h = wins + h * ((p.cap + 15) >> 4);
+                    for (int j = 0; j < n_chunks; ++j) {
                         PROF_WAIT_BEGIN;
-                        mbar_wait(&s_stage_full[s], (uint32_t)(c / UM_NP) & 1u);
+                        mbar_wait(&s_stage_full[stage], sphase);
                         PROF_WAIT_END;
+                        PROF_SEC_BEGIN;
                         tc_fence_after();
-                        const int2 win = s_chunk[s];
-                        const uint32_t st = smem_u32(stages) + (uint32_t)s * UM_STAGE_BYTES;
-                        const uint64_t a_hi = umma_desc(st, 16 * 128, 128), a_lo = umma_desc(st + UM_A_BYTES, 16 * 128, 128);
-                        const uint64_t b_hi = umma_desc(st + 2 * UM_A_BYTES, 32 * 128, 128);
-                        const uint64_t b_lo = umma_desc(st + 2 * UM_A_BYTES + UM_B_BYTES, 32 * 128, 128);
-                        const uint32_t idesc = umma_idesc(win.y);
-                        const uint32_t d = tm + (uint32_t)(h * 256 + win.x);
-                        umma(d, a_hi, b_hi, idesc, j > 0);
-                        umma(d, a_hi, b_lo, idesc, 1);
-                        umma(d, a_lo, b_hi, idesc, 1);
-                        umma_commit(&s_stage_empty[s]);                       // the stage may be refilled
+                        const uint32_t win = win_h[j];
+                        const uint64_t so = (uint64_t)((uint32_t)stage * (UM_STAGE_BYTES >> 4));
+                        const uint32_t idesc = umma_idesc((int)(win >> 16));
+                        const uint32_t d = tm + (uint32_t)(h * 256) + (win & 0xffffu);
+                        PROF_SEC(0);
+                        umma(d, d_a_hi + so, d_b_hi + so, idesc, j > 0);
+                        umma(d, d_a_hi + so, d_b_lo + so, idesc, 1);
+                        umma(d, d_a_lo + so, d_b_hi + so, idesc, 1);
+                        umma_commit(&s_stage_empty[stage]);                   // the stage may be refilled
                         if (j == n_chunks - 1) umma_commit(&s_half_full[h]);  // the half is complete
+                        PROF_SEC(1);
+                        if (++stage == UM_NP) {
+                            stage = 0;
+                            sphase ^= 1u;
+                        }
                     }
-                    __syncwarp();
                 }
+                // (the other lanes only follow the template / half structure)
+                __syncwarp();
             }
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
         PROF_DONE(1);
+        PROF_SEC_STORE(0, 2);
     } else if (warp >= UM_EPI_WARP0 && warp < UM_EPI_WARP0 + UM_EPI) {
         // =============================== epilogue ================================================================
         PROF_DECL;
-        PROF_SEC_DECL;
         const int ew = warp - UM_EPI_WARP0;  // 0..7
         const int q = warp & 3;              // tensor-memory lane quarter this warp may read
         const int ch = ew >> 2;              // of the 32-column tiles of a half this warp takes ct = ch, ch + 2, ...
@@ -539,15 +422,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         const uint32_t tm_q = tm + ((uint32_t)(32 * q) << 16);
         int nbuf = 0;  // staged tiles so far (buffer = nbuf & 1)
         for (int k = 0;; ++k) {
-            const int slot = k & 1;
+            const int slot = k % UM_SLOTS;
             PROF_WAIT_BEGIN;
-            mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            mbar_wait(&s_slot_full[slot], (uint32_t)(k / UM_SLOTS) & 1u);
             PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             const int t = hd->t;
             if (t < 0) break;
             const bool norm = p.normalize && hd->n_live > 0;  // no spot in frame: zeros, returned un-normalised
-            float scale = 1.f, vmax = INFINITY;
+            float scale = 1.f, vmax = INFINITY, clamp = __uint_as_float(0x7fc00000u);
             if (norm) {
                 // ---- pass 1: the template maximum, straight from the accumulators.  (Loops are kept rolled: the four
                 // roles of this kernel share the instruction cache.)
@@ -564,9 +447,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                     if (ch < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * ch), r);
 #pragma unroll 1
                     for (int ct = ch; ct < n_ct; ct += 2) {
-                        PROF_SEC_BEGIN;
                         tmem_wait(r);
-                        PROF_SEC(0);
                         if (row_ok) {
                             if (32 * ct + 32 <= W) {
 #pragma unroll
@@ -583,7 +464,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                             }
                         }
                         if (ct + 2 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 2)), r);
-                        PROF_SEC(1);
                     }
                 }
                 float m = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
@@ -594,9 +474,40 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
 #pragma unroll
                 for (int e = 0; e < UM_EPI; ++e) m = fmaxf(m, s_emax[k & 1][e]);
                 vmax = m;
-                scale = 1.f / vmax;  // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441
+                // np.divide(pattern, np.max(pattern)), simulation2d.py:440-441: the maximum pixel is exactly 1 there.
+                // x * (1 / max) can be 1 ulp off, so the reciprocal is rounded UP (max * scale >= 1 in exact arithmetic,
+                // hence after rounding) and the product clamped to 1.  A NaN clamp leaves everything as computed when
+                // the maximum is not a positive finite number (fminf returns the other operand).
+                scale = 1.f / vmax;
+                if (vmax > 0.f && vmax < INFINITY) {
+                    if (scale * vmax < 1.f) scale = __uint_as_float(__float_as_uint(scale) + 1u);
+                    clamp = 1.f;
+                }
             }
-            // ---- pass 2: scale, stage, store
+            // ---- pass 2: scale, stage, store.  Two register sets alternate (the load of the next tile is in flight
+            // while this one is scaled and staged); `stage_tile` is the per-tile tail.
+            auto stage_tile = [&](const uint32_t (&r)[32], int ct, int row0) {
+                // the copy that last read this buffer has finished reading it
+                if (elect_one()) {
+                    if (epi_bufs == 2)
+                        tma_store_wait_read<1>();
+                    else
+                        tma_store_wait_read<0>();
+                }
+                __syncwarp();
+                const uint32_t buf = tile_s + (uint32_t)(epi_bufs == 2 ? (nbuf & 1) : 0) * UM_TILE_BYTES;
+                // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
+                                 "f"(fminf(__uint_as_float(r[4 * j]) * scale, clamp)), "f"(fminf(__uint_as_float(r[4 * j + 1]) * scale, clamp)),
+                                 "f"(fminf(__uint_as_float(r[4 * j + 2]) * scale, clamp)), "f"(fminf(__uint_as_float(r[4 * j + 3]) * scale, clamp))
+                                 : "memory");
+                proxy_fence();
+                __syncwarp();
+                if (elect_one()) tma_store_tile(&tmap, buf, 32 * ct, row0, t);
+                ++nbuf;
+            };
 #pragma unroll 1
             for (int h = 0; h < n_halves; ++h) {
                 if (!norm) {
@@ -607,45 +518,18 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                 }
                 const int row0 = 128 * h + 32 * q;  // first image row of this warp's 32 lanes
                 if (row0 < H && ch < n_ct) {
-                    uint32_t r[32];
-                    tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * ch), r);
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * ch), ra);
 #pragma unroll 1
-                    for (int ct = ch; ct < n_ct; ct += 2) {
-                        PROF_SEC_BEGIN;
-                        tmem_wait(r);
-                        PROF_SEC(2);
-                        float v[32];
-                        // numpy divides, so the maximum pixel is exactly 1 while x * (1 / max) can be 1 ulp off: pin it
-                        // (vmax = +inf when the template is not normalised: never equal)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = __uint_as_float(r[j]);
-                            v[j] = (x == vmax) ? 1.0f : x * scale;
+                    for (int ct = ch; ct < n_ct; ct += 4) {
+                        if (ct + 2 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 2)), rb);
+                        tmem_wait(ra);  // (all loads issued so far: the one just issued is short)
+                        stage_tile(ra, ct, row0);
+                        if (ct + 2 < n_ct) {
+                            if (ct + 4 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 4)), ra);
+                            tmem_wait(rb);
+                            stage_tile(rb, ct + 2, row0);
                         }
-                        if (ct + 2 < n_ct) tmem_ld32_issue(tm_q + (uint32_t)(h * 256 + 32 * (ct + 2)), r);
-                        PROF_SEC(3);
-                        // the copy that last read this buffer has finished reading it
-                        if (lane == 0) {
-                            if (epi_bufs == 2)
-                                tma_store_wait_read<1>();
-                            else
-                                tma_store_wait_read<0>();
-                        }
-                        __syncwarp();
-                        PROF_SEC(4);
-                        const uint32_t buf = tile_s + (uint32_t)(epi_bufs == 2 ? (nbuf & 1) : 0) * UM_TILE_BYTES;
-                        // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
-                                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                         : "memory");
-                        proxy_fence();
-                        __syncwarp();
-                        PROF_SEC(5);
-                        if (lane == 0) tma_store_tile(&tmap, buf, 32 * ct, row0, t);
-                        ++nbuf;
-                        PROF_SEC(6);
                     }
                 }
                 // this warp's reads of the half are complete: hand it back to the MMA warp
@@ -656,14 +540,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
-        if (lane == 0) tma_store_wait_read<0>();
-        if (ew == 0) {
-            PROF_DONE(2);
-            PROF_SEC_DONE;
-        }
+        if (elect_one()) tma_store_wait_read<0>();
+        if (ew == 0) { PROF_DONE(2); }
     } else {
         // =============================== operand producers =======================================================
         PROF_DECL;
+        PROF_SEC_DECL;
         const int pi = warp < UM_EPI_WARP0 ? warp - 2 : warp - (UM_EPI_WARP0 + UM_EPI) + 2;  // 0..7
         const int pw = pi >> 1, kh = pi & 1;  // team (= its stage), and the K group (spots 8 kh .. 8 kh + 7) this warp writes
         const uint32_t st = smem_u32(stages) + (uint32_t)pw * UM_STAGE_BYTES;
@@ -678,9 +560,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         const uint32_t b_hi = st + 2 * UM_A_BYTES + (uint32_t)(kh * (32 * 128) + k8 * 16), b_lo = b_hi + UM_B_BYTES;
         int c = 0;
         for (int k = 0;; ++k) {
-            const int slot = k & 1;
+            const int slot = k % UM_SLOTS;
             PROF_WAIT_BEGIN;
-            mbar_wait(&s_slot_full[slot], (uint32_t)(k >> 1) & 1u);
+            mbar_wait(&s_slot_full[slot], (uint32_t)(k / UM_SLOTS) & 1u);
             PROF_WAIT_END;
             const UmHeader *hd = slot_header(slot);
             if (hd->t < 0) break;
@@ -689,107 +571,77 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
                 const int n_h = hd->n_half[h];
                 const int n_chunks = max(1, (n_h + 15) >> 4);
                 const uint32_t list_s = smem_u32(slot_list(slot, h));
+                const uint32_t win_s = smem_u32(slots + (size_t)slot * slot_bytes + umma_windows_offset(p.cap));
+                const int win_stride = (p.cap + 15) >> 4;
                 for (int j = 0; j < n_chunks; ++j, ++c) {
                     if (c % UM_NP != pw) continue;
-                    // this lane's spot of the chunk; the column window needs the extent of all 16
-                    const int li = 16 * j + 8 * kh + k8, li_other = 16 * j + 8 * (kh ^ 1) + k8;
+                    PROF_SEC_BEGIN;
+                    // this lane's spot of the chunk and the chunk's column window (render_prep.cu)
+                    const int li = 16 * j + 8 * kh + k8;
                     const bool ok = li < n_h;
                     int cx = 0, cy = 0;
                     float am = 0.f;
-                    int xmin = 1 << 20, xmax = -1;
                     if (ok) {
                         const uint2 r = lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li));
                         cx = (int)(r.x & 0xffffu);
                         cy = (int)(r.x >> 16);
                         am = __uint_as_float(r.y);
-                        xmin = xmax = cx;
                     }
-                    // column window of the chunk (the first chunk of a half covers every column: it zeroes them)
-                    int col0 = 0, ncols = Wp;
-                    if (window && j > 0) {
-                        if (li_other < n_h) {
-                            const int ox = (int)(lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li_other)).x & 0xffffu);
-                            xmin = min(xmin, ox);
-                            xmax = max(xmax, ox);
-                        }
-                        xmin = -warp_max(-xmin);
-                        xmax = warp_max(xmax);
-                        col0 = max(0, xmin - R) & ~15;
-                        ncols = ((min(W, xmax + R + 1) - col0) + 15) & ~15;
-                    }
+                    const uint32_t win = lds32v(win_s + 4u * (uint32_t)(h * win_stride + j));
+                    const int col0 = (int)(win & 0xffffu), ncols = (int)(win >> 16);
+                    PROF_SEC(2);
                     PROF_WAIT_BEGIN;
                     mbar_wait(&s_stage_empty[pw], ((uint32_t)(c / UM_NP) & 1u) ^ 1u);
                     PROF_WAIT_END;
-                    // ---- A: a_s Wy_s[y], rows 128 h + 8 g .. + 7.  scipy's mode="reflect" adds the mirror images of the
-                    // spot at -c - 1 (spots within R of the low border) and 2 n - 1 - c (high border); they only reach the
-                    // few groups next to that border, so most units are one table read
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int g = gq + 4 * i, y_lo = 128 * h + 8 * g;
-                        if (ok && y_lo + 7 >= cy - R && y_lo <= cy + R) {
-                            const uint32_t a = fetch_addr(L, y_lo + L.bias - cy);
-                            float4 w0 = lds128(a), w1 = lds128(a + 16u);
-                            const int d_lo = y_lo + cy + 1, d_hi = y_lo + cy + 1 - 2 * H;
-                            if (d_lo <= R) {
-                                const uint32_t a2 = fetch_addr(L, d_lo + L.bias);
-                                w0 = add4(w0, lds128(a2));
-                                w1 = add4(w1, lds128(a2 + 16u));
-                            }
-                            if (d_hi + 7 >= -R && d_hi <= R) {
-                                const uint32_t a3 = fetch_addr(L, d_hi + L.bias);
-                                w0 = add4(w0, lds128(a3));
-                                w1 = add4(w1, lds128(a3 + 16u));
-                            }
-                            store_split8(a_hi + 128u * g, a_lo + 128u * g, w0, w1, am);
-                        } else {
-                            sts128(a_hi + 128u * g, 0u, 0u, 0u, 0u);
-                            sts128(a_lo + 128u * g, 0u, 0u, 0u, 0u);
-                        }
-                    }
-                    // ---- B: Wx_s[x], columns col0 + 8 g .. + 7: a shifted copy of the pre-split table, except for the
-                    // units a mirror image reaches
+                    PROF_SEC_BEGIN;
+                    // ---- A
+                    const bool lo_half = 128 * h < R, hi_half = 128 * h + 127 >= H - R;
+                    if (lo_half && hi_half)
+                        produce_a<true, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else if (lo_half)
+                        produce_a<true, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else if (hi_half)
+                        produce_a<false, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else
+                        produce_a<false, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    PROF_SEC(3);
+                    // ---- B: Wx_s[x], columns col0 + 8 g .. + 7.  Blocks of four units next to a border take the float32
+                    // path with the mirror images; everything in between is a shifted copy of the pre-split table
+                    const int n_blk = ncols >> 5, n_units = ncols >> 3;  // (ncols is a multiple of 16: the last block may be half)
+                    int g0 = 0;
+#pragma unroll 1
+                    for (; 8 * g0 < ncols && col0 + 8 * g0 < R; g0 += 4)
+                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
 #pragma unroll 2
-                    for (int g = gq; g < (ncols >> 3); g += 4) {
-                        const int x_lo = col0 + 8 * g;
-                        if (ok && x_lo + 7 >= cx - R && x_lo <= cx + R) {
-                            const int d_lo = x_lo + cx + 1, d_hi = x_lo + cx + 1 - 2 * W;
-                            const bool m_lo = d_lo <= R, m_hi = d_hi + 7 >= -R && d_hi <= R;
-                            if (m_lo || m_hi) {
-                                const uint32_t a1 = fetch_addr(L, x_lo + L.bias - cx);
-                                float4 w0 = lds128(a1), w1 = lds128(a1 + 16u);
-                                if (m_lo) {
-                                    const uint32_t a2 = fetch_addr(L, d_lo + L.bias);
-                                    w0 = add4(w0, lds128(a2));
-                                    w1 = add4(w1, lds128(a2 + 16u));
-                                }
-                                if (m_hi) {
-                                    const uint32_t a3 = fetch_addr(L, d_hi + L.bias);
-                                    w0 = add4(w0, lds128(a3));
-                                    w1 = add4(w1, lds128(a3 + 16u));
-                                }
-                                store_split8(b_hi + 128u * g, b_lo + 128u * g, w0, w1, 1.0f);
-                            } else {
-                                const int a = x_lo - cx + R + UM_BPAD;
-                                const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
-                                const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
-                                sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
-                                sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
-                            }
-                        } else {
-                            sts128(b_hi + 128u * g, 0u, 0u, 0u, 0u);
-                            sts128(b_lo + 128u * g, 0u, 0u, 0u, 0u);
+                    for (; 8 * g0 < ncols && col0 + 8 * g0 + 31 < W - R; g0 += 4) {
+                        const int g = g0 + gq, x_lo = col0 + 8 * g;
+                        const bool hit = ok && x_lo + 7 >= cx - R && x_lo <= cx + R;
+                        const int a = hit ? x_lo - cx + R + UM_BPAD : 0;  // (entry 0 of copy 0 is all zero)
+                        const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
+                        const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
+                        if (g < n_units) {
+                            sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
+                            sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
                         }
                     }
-                    if (kh == 0 && lane == 0) s_chunk[pw] = make_int2(col0, ncols);
+#pragma unroll 1
+                    for (; 8 * g0 < ncols; g0 += 4)
+                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
+                    (void)n_blk;
+                    PROF_SEC(4);
                     proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s_stage_full[pw]);
+                    PROF_SEC(5);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
-        if (pi == 0) { PROF_DONE(3); }
+        if (pi == 0) {
+            PROF_DONE(3);
+            PROF_SEC_STORE(2, 4);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -815,26 +667,22 @@ static EncodeTiledFn encode_tiled() {
     return reinterpret_cast<EncodeTiledFn>(fn);
 }
 
+int launch_render_prepare(const RenderParams &p, unsigned char *records, int window, cudaStream_t st);
+
 // Returns 1 if the tensor-core kernel was launched, 0 if the configuration is not eligible, < 0 on error.
-int launch_render_umma(RenderParams p, cudaStream_t st) {
+// `records`: n_tmpl * umma_record_bytes(cap) bytes of device scratch (the prepared templates).
+int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st) {
     if (p.H > 256 || p.W > 256 || (p.W & 3) != 0 || p.cap > UM_MAX_CAP || p.radius >= p.W || p.radius >= p.H || p.radius > 120)
         return 0;
     EncodeTiledFn encode = encode_tiled();
     if (encode == nullptr) return 0;
     const int n8 = um_n8(p.radius);
-    const int slot_bytes = (32 + p.cap * 8 + 2 * p.cap * 2 + 15) & ~15;
-    // spot rows are staged through shared memory whenever they are 16-byte granular (the front warp must not wait for
-    // global loads behind a saturated store stream)
-    p.stage = ((p.cap & 1) == 0 && (reinterpret_cast<uintptr_t>(p.xyz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.intensity) & 15) == 0 &&
-               option(OPT_RENDER_NOSTAGE) <= 0)
-                  ? 1
-                  : 0;
-    const int front_bytes = (int)(((p.stage ? (size_t)p.cap * 32 : 0) + (size_t)p.cap * 8 + (size_t)8 * 33 * 4 + 15) & ~(size_t)15);
+    const int slot_bytes = umma_record_bytes(p.cap);
     // two staged tiles per epilogue warp when they fit (large capacities are tensor-pipe bound anyway)
     int epi_bufs = 2;
     auto smem_for = [&](int bufs) {
         return (size_t)UM_NP * UM_STAGE_BYTES + (size_t)UM_EPI * bufs * UM_TILE_BYTES + lut_smem_bytes(p.n4) + (size_t)2 * 8 * n8 * 16 +
-               front_bytes + (size_t)2 * slot_bytes;
+               (size_t)UM_SLOTS * slot_bytes;
     };
     if (smem_for(2) > 226 * 1024) epi_bufs = 1;
     const size_t smem = smem_for(epi_bufs);
@@ -851,11 +699,13 @@ int launch_render_umma(RenderParams p, cudaStream_t st) {
         set_error("ds_render (tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)cr);
         return -2;
     }
-    cudaFuncSetAttribute(render_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const int window = option(OPT_RENDER_UMMA_WINDOW) == 0 ? 0 : 1;
+    const int rc0 = launch_render_prepare(p, records, window, st);
+    if (rc0 != 0) return rc0;
+    cudaFuncSetAttribute(render_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const int sms = num_sms();
     const int grid = p.n_tmpl < sms ? p.n_tmpl : sms;
-    render_umma_kernel<<<grid, UM_THREADS, smem, st>>>(p, tmap, slot_bytes, front_bytes, window, epi_bufs);
+    render_umma_kernel<<<grid, UM_THREADS, smem, st>>>(p, tmap, records, slot_bytes, window, epi_bufs);
     const int rc = check_launch("ds_render (tcgen05)");
     return rc == 0 ? 1 : rc;
 }

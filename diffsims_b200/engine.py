@@ -350,16 +350,19 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
 # ----------------------------------------------------------------------------------------------
 # K3
 # ----------------------------------------------------------------------------------------------
-_TICKETS = {}
+_SCRATCH = {}
 
 
-def _ticket(dev):
-    """Two zeroed int32 words per (device, stream) that ds_render uses to hand templates to CTAs; every
-    launch leaves them zero, so they are allocated once."""
+def _render_scratch(dev, n, cap):
+    """Device scratch of ds_render (ticket words + prepared template records), one buffer per (device, stream),
+    grown on demand.  Streams under CUDA-graph capture get their own allocation from the graph's pool."""
+    need = int(_cabi.lib().ds_render_scratch_bytes(int(n), int(cap)))
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(need, dtype=torch.uint8, device=dev)
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    t = _TICKETS.get(key)
-    if t is None:
-        t = _TICKETS[key] = torch.zeros(2, dtype=torch.int32, device=dev)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < need:
+        t = _SCRATCH[key] = torch.empty(max(need, 4096), dtype=torch.uint8, device=dev)
     return t
 
 
@@ -385,7 +388,7 @@ def render(count, xyz, intensity, shape, sigma, calibration, center, in_plane_an
         _stream(), n, cap, _cabi.ptr(count), _cabi.ptr(xyz), _cabi.ptr(intensity), H, W,
         float(calibration), float(center[0]), float(center[1]), float(in_plane_angle), int(bool(mirrored)),
         (2 if fast == "bare" else int(bool(fast))), float(sigma), gaussian_radius(sigma), float(clip_threshold), int(bool(normalize)),
-        _cabi.ptr(out), _cabi.ptr(_ticket(dev)), 0.0 if mean_spots is None else float(mean_spots))
+        _cabi.ptr(out), _cabi.ptr(_render_scratch(dev, n, cap)), 0.0 if mean_spots is None else float(mean_spots))
     _cabi.check(rc, "ds_render")
     return out
 

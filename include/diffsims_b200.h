@@ -166,6 +166,7 @@ int ds_simulate(void *stream,
  * same computation for square shapes: pattern[x, y] = I followed by .T.)
  * images[n_tmpl][H][W] float32.  Rows of xyz are [cap][3] doubles (z ignored).
  */
+int64_t ds_render_scratch_bytes(int32_t n_tmpl, int32_t cap);
 int ds_render(void *stream,
               int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
               const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
@@ -174,8 +175,10 @@ int ds_render(void *stream,
               int32_t fast, double sigma, int32_t radius,
               double clip_threshold, int32_t normalize,
               float *images /*[n_tmpl][H][W]*/,
-              int32_t *ticket /*[2] device scratch words, zeroed by the call itself on `stream`; one pair per
-                                 concurrently used stream (templates are handed to CTAs dynamically)*/,
+              void *scratch /*device scratch of ds_render_scratch_bytes(n_tmpl, cap) bytes, 16-byte aligned, contents
+                              irrelevant on entry; one buffer per concurrently used stream.  Holds the ticket words
+                              that hand templates to CTAs dynamically and, for the tcgen05 path, one prepared record
+                              per template (live spots sorted by detector column + per-half lists)*/,
               double mean_spots_hint /*expected reflections per template, <= 0 if unknown: only tunes the
                                        schedule (front warps per CTA), never the result*/);
 

@@ -39,5 +39,5 @@ for name, ph, kv, rr, s_max, sigma, n in CONFIGS:
     per = n / 148.0
     print(f"{name:22s} templates/CTA ~{per:6.1f} | " + " | ".join(
         f"{r}: {v[i, 0] / per:8.0f} cyc/tmpl, waiting {v[i, 1] / max(v[i, 0], 1):4.0%}" for i, r in enumerate(("front", "mma", "epilogue", "producer0"))))
-    names = ("pass1-ldtm", "pass1-rest", "pass2-ldtm", "pass2-scale", "pass2-buf-free", "pass2-sts+fence", "pass2-issue", "-")
-    print("    first epilogue warp, cycles per template: " + ", ".join(f"{nm} {sec[i] / per:7.0f}" for i, nm in enumerate(names)))
+    names = ("mma:desc", "mma:issue+commit", "prod:spot+window", "prod:A", "prod:B", "prod:fence+arrive", "-", "-")
+    print("    MMA lane / producer warp 0, cycles per template: " + ", ".join(f"{nm} {sec[i] / per:7.0f}" for i, nm in enumerate(names)))
