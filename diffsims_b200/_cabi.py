@@ -15,8 +15,8 @@ _lib = None
 
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors", "ds_pack_gtable",
-           "ds_simulate", "ds_render_scratch_bytes", "ds_render", "ds_polar_flatten", "ds_library_pixel_coords",
-           "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points")
+           "ds_simulate", "ds_render_scratch_bytes", "ds_render_launch_count", "ds_render", "ds_pack_csr", "ds_polar_flatten", "ds_library_pixel_coords",
+           "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points", "ds_so3_grid_num_blocks", "ds_so3_grid")
 ABI_VERSION = 2
 
 
@@ -45,20 +45,25 @@ def lib():
     L.ds_pack_gtable.argtypes = [P, I, P, P, P, I, D]
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P, D]
+    L.ds_pack_csr.argtypes = [P, I, I, P, P, P, P, P, P, P, P]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
     L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]
     L.ds_beam_grid.argtypes = [P, I, I, P, I, P, D, P, P, P, P]
     L.ds_beam_grid_num_blocks.argtypes = [I]
     L.ds_beam_points.argtypes = [P, I, ctypes.c_int64, P, I, P, D, P, P, P, P]
     L.ds_beam_points_num_blocks.argtypes = [ctypes.c_int64]
+    L.ds_so3_grid.argtypes = [P, I, I, I, I, P, D, P, P, P, P, P]
+    L.ds_so3_grid_num_blocks.argtypes = [I]
     L.ds_set_option.argtypes = [c_char_p, I]
     L.ds_get_option.argtypes = [c_char_p, P]
     for s in SYMBOLS[2:]:
         getattr(L, s).restype = c_int32
+    L.ds_render_launch_count.argtypes = [I, I, I, I, I, D]
     L.ds_render_scratch_bytes.argtypes = [I, I]
     L.ds_render_scratch_bytes.restype = ctypes.c_int64
     L.ds_beam_grid_num_blocks.restype = ctypes.c_int64
     L.ds_beam_points_num_blocks.restype = ctypes.c_int64
+    L.ds_so3_grid_num_blocks.restype = ctypes.c_int64
     _lib = L
     return L
 

@@ -84,7 +84,43 @@ __global__ void pixel_coords_kernel(int n_tmpl, int cap, const int *__restrict__
     out[2 * i + 1] = py;
 }
 
+// Padded rows -> CSR: template t's count[t] reflections go to offsets[t] .. offsets[t + 1] - 1 (the "packed spot
+// lists" a sharded library gathers and a host consumer receives: ~40 bytes per reflection instead of `cap` slots).
+__global__ void pack_csr_kernel(int n_tmpl, int cap, const int *__restrict__ count, const long long *__restrict__ offsets,
+                                const int *__restrict__ g_index, const double *__restrict__ xyz,
+                                const double *__restrict__ intensity, int *__restrict__ g_out, double *__restrict__ xyz_out,
+                                double *__restrict__ i_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_tmpl) return;
+    const int n = min(count[warp], cap);
+    const size_t row = (size_t)warp * cap;
+    const long long o = offsets[warp];
+    if (g_out != nullptr)
+        for (int j = lane; j < n; j += 32) g_out[o + j] = g_index[row + j];
+    if (i_out != nullptr)
+        for (int j = lane; j < n; j += 32) i_out[o + j] = intensity[row + j];
+    if (xyz_out != nullptr)
+        for (int j = lane; j < 3 * n; j += 32) xyz_out[3 * o + j] = xyz[3 * row + j];
+}
+
 }  // namespace ds
+
+extern "C" int ds_pack_csr(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const int64_t *offsets,
+                           const int32_t *g_index, const double *xyz, const double *intensity, int32_t *g_index_out,
+                           double *xyz_out, double *intensity_out) {
+    using namespace ds;
+    DS_REQUIRE(n_tmpl >= 0 && cap > 0, "ds_pack_csr: bad sizes");
+    DS_REQUIRE(count != nullptr && offsets != nullptr, "ds_pack_csr: count and offsets are required");
+    DS_REQUIRE((g_index_out == nullptr || g_index != nullptr) && (xyz_out == nullptr || xyz != nullptr) &&
+                   (intensity_out == nullptr || intensity != nullptr),
+               "ds_pack_csr: an output was requested without its input");
+    if (n_tmpl == 0) return 0;
+    const int threads = 256, warps = threads / 32;
+    pack_csr_kernel<<<(n_tmpl + warps - 1) / warps, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_tmpl, cap, count, reinterpret_cast<const long long *>(offsets), g_index, xyz, intensity, g_index_out, xyz_out,
+        intensity_out);
+    return check_launch("ds_pack_csr");
+}
 
 extern "C" int ds_library_pixel_coords(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count,
                                        const double *xyz, double calibration_x, double calibration_y,

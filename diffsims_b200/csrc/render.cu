@@ -24,6 +24,12 @@ namespace ds {
 
 int launch_render_pipelined(RenderParams p, cudaStream_t st);
 int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st);
+bool umma_eligible(int H, int W, int cap, int radius);
+// the dispatch rule of ds_render for the tcgen05 path (shared with ds_render_launch_count)
+static bool wants_umma(int cap, double mean_spots_hint) {
+    const int um = option(OPT_RENDER_UMMA);
+    return um >= 0 ? um != 0 : (mean_spots_hint > 0.0 ? mean_spots_hint >= 16.0 : cap >= 96);
+}
 
 // A "group" of G warps (G = 1, 2, 4 or 8) owns one template at a time; a CTA holds 8 / G groups and is
 // persistent (templates are drawn from a global ticket).  G = 1 keeps 8 independent templates in flight per
@@ -381,6 +387,15 @@ static int launch_render(const RenderParams &p, int group_bytes, size_t lut_byte
 
 }  // namespace ds
 
+extern "C" int ds_render_launch_count(int32_t cap, int32_t H, int32_t W, int32_t radius, int32_t fast, double mean_spots_hint) {
+    using namespace ds;
+    const bool wide = fast == 1 && (radius >= W || radius >= H);
+    const int g_opt = option(OPT_RENDER_GROUP);
+    const bool g_forced = g_opt == 1 || g_opt == 2 || g_opt == 4 || g_opt == 8;
+    if (fast == 1 && !wide && !g_forced && wants_umma(cap, mean_spots_hint) && umma_eligible(H, W, cap, radius)) return 2;
+    return 1;
+}
+
 extern "C" int64_t ds_render_scratch_bytes(int32_t n_tmpl, int32_t cap) {
     if (n_tmpl < 0 || cap < 0) return -1;
     return 16 + (int64_t)n_tmpl * ds::umma_record_bytes(cap);
@@ -484,9 +499,7 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     // option render_umma = 0 / 1 forces it off / on.  Measured cross-over on B200 (profiles/r02_k3_variants*.txt): the
     // float32 pipelined kernel wins below ~16 reflections per template (sigma 10), the tcgen05 kernel above.
     if (fast && !wide && !g_forced) {
-        const int um = option(OPT_RENDER_UMMA);
-        const bool want_umma = um >= 0 ? um != 0 : (mean_spots_hint > 0.0 ? mean_spots_hint >= 16.0 : cap >= 96);
-        if (want_umma) {
+        if (wants_umma(cap, mean_spots_hint)) {
             const int rc = launch_render_umma(p, static_cast<unsigned char *>(scratch) + 16, st);
             if (rc != 0) return rc < 0 ? rc : 0;
         }

@@ -671,9 +671,12 @@ int launch_render_prepare(const RenderParams &p, unsigned char *records, int win
 
 // Returns 1 if the tensor-core kernel was launched, 0 if the configuration is not eligible, < 0 on error.
 // `records`: n_tmpl * umma_record_bytes(cap) bytes of device scratch (the prepared templates).
+bool umma_eligible(int H, int W, int cap, int radius) {
+    return !(H > 256 || W > 256 || (W & 3) != 0 || cap > UM_MAX_CAP || radius >= W || radius >= H || radius > 120);
+}
+
 int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st) {
-    if (p.H > 256 || p.W > 256 || (p.W & 3) != 0 || p.cap > UM_MAX_CAP || p.radius >= p.W || p.radius >= p.H || p.radius > 120)
-        return 0;
+    if (!umma_eligible(p.H, p.W, p.cap, p.radius)) return 0;
     EncodeTiledFn encode = encode_tiled();
     if (encode == nullptr) return 0;
     const int n8 = um_n8(p.radius);

@@ -366,6 +366,14 @@ def _render_scratch(dev, n, cap):
     return t
 
 
+def render_launch_count(cap, shape, sigma, fast=True, mean_spots=None):
+    """How many kernels ds_render launches for this configuration (1, or 2 when the tcgen05 path with its prepare
+    pass is taken) -- the library's own dispatch rule, for honest launch accounting."""
+    return int(_cabi.lib().ds_render_launch_count(int(cap), int(shape[0]), int(shape[1]), gaussian_radius(sigma),
+                                                  2 if fast == "bare" else int(bool(fast)),
+                                                  0.0 if mean_spots is None else float(mean_spots)))
+
+
 def gaussian_radius(sigma, truncate=4.0):
     """scipy.ndimage.gaussian_filter1d: lw = int(truncate * sd + 0.5)."""
     return int(truncate * float(sigma) + 0.5)

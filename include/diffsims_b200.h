@@ -167,6 +167,9 @@ int ds_simulate(void *stream,
  * images[n_tmpl][H][W] float32.  Rows of xyz are [cap][3] doubles (z ignored).
  */
 int64_t ds_render_scratch_bytes(int32_t n_tmpl, int32_t cap);
+/* number of kernels ds_render launches for a configuration (1, or 2 when the tcgen05 path runs its per-template
+   prepare pass first); the dispatch rule itself, exported for launch accounting */
+int ds_render_launch_count(int32_t cap, int32_t H, int32_t W, int32_t radius, int32_t fast, double mean_spots_hint);
 int ds_render(void *stream,
               int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
               const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
@@ -196,6 +199,19 @@ int ds_polar_flatten(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *c
                      int32_t max_spots, int32_t n_radial, const double *radial_axes /*[n_radial] or NULL*/,
                      int32_t n_azimuthal, const double *azimuthal_axes /*[n_azimuthal] or NULL*/,
                      double *r_out, double *theta_out, double *intensity_out);
+
+/*
+ * Padded per-rotation rows (the output of ds_simulate) -> CSR: template t's min(count[t], cap) reflections are
+ * copied to offsets[t] .. offsets[t + 1] - 1 of the packed arrays (offsets: int64 [n_tmpl + 1], the exclusive
+ * prefix sums of the counts).  This is the "packed spot list" form of a library: what a sharded build gathers
+ * at its end (the loops it replaces are diffsims/generators/simulation_generator.py:198,
+ * :211 and diffsims/generators/library_generator.py:107, :117) and what a host consumer of
+ * calculate_diffraction2d receives.  Any of the three outputs may be NULL.
+ */
+int ds_pack_csr(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count /*[n_tmpl]*/,
+                const int64_t *offsets /*[n_tmpl + 1]*/, const int32_t *g_index /*[n_tmpl][cap]*/,
+                const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
+                int32_t *g_index_out /*[total]*/, double *xyz_out /*[total][3]*/, double *intensity_out /*[total]*/);
 
 /*
  * Pixel coordinates of an old-api template library: rint((xy + offset) / calibration + half_shape) as int32
@@ -235,6 +251,23 @@ int64_t ds_beam_points_num_blocks(int64_t n_points);
 int ds_beam_points(void *stream, int32_t pass, int64_t n_points, const double *points, int32_t mode,
                    const double *normals_host, double epsilon, int32_t *block_counts,
                    const int64_t *block_offsets, double *euler_deg, double *quat_active);
+
+/*
+ * Rotation-list producer over SO(3): the cubochoric equal-volume grid of rotations ((2 n_steps)^3 cell-centred points
+ * of the cube of edge pi^(2/3), mapped to unit quaternions) cropped to the fundamental zone of a proper point group
+ * (mode 1: sym_quats_host[n_sym][4], HOST pointer, <= 24 operations; a rotation is kept iff none of its symmetric
+ * equivalents has a smaller rotation angle), to rotation angles <= max_angle_rad (mode 2) or not at all (mode 0),
+ * optionally composed with a centre rotation (centre_quat_host[4] or NULL: q_out = centre * q).
+ * Replaces get_fundamental_zone_grid / get_local_grid (diffsims/generators/rotation_list_generators.py:85-134), i.e.
+ * orix.sampling.get_sample_fundamental / get_sample_local (third party, source absent: parity with orix's point
+ * lists is UNPINNED; the algorithm is the published one, see csrc/so3_grid.cu).  Order-preserving compaction in two
+ * passes over ds_so3_grid_num_blocks(n_steps) blocks exactly as ds_beam_grid.  euler_deg [n][3] (Bunge, degrees) and
+ * quat_active [n][4] (the conjugates, what ds_simulate consumes) may be NULL.
+ */
+int64_t ds_so3_grid_num_blocks(int32_t n_steps);
+int ds_so3_grid(void *stream, int32_t pass, int32_t n_steps, int32_t mode, int32_t n_sym,
+                const double *sym_quats_host, double max_angle_rad, const double *centre_quat_host,
+                int32_t *block_counts, const int64_t *block_offsets, double *euler_deg, double *quat_active);
 
 #ifdef __cplusplus
 }
