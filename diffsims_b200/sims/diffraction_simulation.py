@@ -134,12 +134,16 @@ class DiffractionSimulation:
         the new api for square shapes (non-square shapes index out of bounds there)."""
         if self.calibration is None:
             raise Exception("Pixel calibration is not set!")
-        if self.calibration[0] != self.calibration[1] or shape[0] != shape[1]:
-            raise NotImplementedError("anisotropic calibration / non-square shapes are not supported")
+        if shape[0] != shape[1]:
+            # (the reference indexes pattern[x, y] on a `shape` array and transposes: out of bounds / transposed output
+            # for non-square shapes)
+            raise NotImplementedError("non-square shapes are not supported")
         if direct_beam_position is None:
             direct_beam_position = (shape[1] // 2, shape[0] // 2)
         xyz = np.zeros((self.coordinates.shape[0], 3))
-        xyz[:, :2] = self.coordinates[:, :2] + self.offset
+        # per-axis calibration (cx, cy), :141-147: the division is done here in float64 exactly as the reference's
+        # calibrated_coordinates does it, and K3 runs with a calibration of 1 (x / 1.0 is exact)
+        xyz[:, :2] = (self.coordinates[:, :2] + self.offset) / self.calibration
         n = xyz.shape[0]
         dev = engine.device()
         cap = max(32, (n + 31) // 32 * 32)
@@ -148,6 +152,6 @@ class DiffractionSimulation:
         I = np.zeros((1, cap))
         I[0, :n] = self.intensities
         img = engine.render(torch.tensor([n], dtype=torch.int32, device=dev), torch.as_tensor(X, device=dev),
-                            torch.as_tensor(I, device=dev), shape, sigma, float(self.calibration[0]),
+                            torch.as_tensor(I, device=dev), shape, sigma, 1.0,
                             direct_beam_position, in_plane_angle, mirrored, True, True, 1.0)
         return img[0].cpu().numpy().astype(np.float64)

@@ -139,5 +139,33 @@ out["vertices_icosahedral_3deg"] = smg.get_icosahedral_mesh_vertices(3)
 out["vertices_random_4deg_seed3"] = smg.get_random_sphere_vertices(4, seed=3)
 np.savez_compressed(HERE / "beam_grid.npz", **out)
 
+# ---------------------------------------------------------------- round-2 closures (old-api DiffractionSimulation)
+# (a) per-axis calibration (sims/diffraction_simulation.py:141-147); (b) knife-edge pixels: spots whose pixel coordinates are
+# exact integers, where the reference's r cos(atan2(y, x) + a) + cx round trip decides the truncation by its own ulp noise
+dsim = ns.diffraction_simulation
+out = {}
+c = cases.ED_CASES["si"]
+st = cases.structure(c["structure"])
+gen = dg.DiffractionGenerator(c["kv"])
+sim = gen.calculate_ed_data(st, c["rr"], rotation=c["eulers"][3], with_direct_beam=True, max_excitation_error=c["s_max"])
+for tag, cal, kw in (("aniso", (1.0 / 128, 1.0 / 100), dict()),
+                     ("aniso_rot", (0.009, 0.0065), dict(in_plane_angle=30.0, mirrored=True))):
+    sim.calibration = cal
+    out[f"{tag}_coords"] = sim.coordinates
+    out[f"{tag}_intensities"] = sim.intensities
+    out[f"{tag}_calibration"] = np.array(cal)
+    out[f"{tag}_pattern"] = sim.get_diffraction_pattern(shape=(256, 256), sigma=6, **kw).astype(np.float32)
+cal = 0.01
+ij = np.array([(i, j) for i in range(-4, 5) for j in range(-4, 5)], dtype=float)
+coords = np.concatenate([ij * 25 * cal, np.zeros((len(ij), 1))], axis=1)          # pixels at exact multiples of 25
+knife = dsim.DiffractionSimulation(coords, intensities=1.0 + np.arange(len(ij)) % 7, calibration=cal)
+out["knife_coords"] = coords
+out["knife_intensities"] = knife.intensities
+for ang in (0.0, 90.0, 45.0):
+    t = knife._get_transformed_coordinates(ang, (128, 128), False, units="pixel")
+    out[f"knife_pixels_{int(ang)}"] = t[:, :2]
+    out[f"knife_pattern_{int(ang)}"] = knife.get_diffraction_pattern(shape=(256, 256), sigma=2, in_plane_angle=ang).astype(np.float32)
+np.savez_compressed(HERE / "closures.npz", **out)
+
 for f in sorted(HERE.glob("*.npz")):
     print(f.name, f.stat().st_size)

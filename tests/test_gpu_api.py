@@ -624,3 +624,147 @@ def test_library_builder_capacity_covers_the_pre_cut_count():
 def engine_device():
     from diffsims_b200 import engine
     return engine.device()
+
+
+# --------------------------------------------------------------------------- round-2 closures
+@pytest.mark.parametrize("tag,kw", [("aniso", {}), ("aniso_rot", dict(in_plane_angle=30.0, mirrored=True))])
+def test_old_api_pattern_with_per_axis_calibration_matches_reference_golden(golden_dir, tag, kw):
+    """DiffractionSimulation.get_diffraction_pattern with calibration = (cx, cy), diffsims/sims/diffraction_simulation.py
+    :141-147, :296-354, against the reference executed by tests/golden/make_golden.py."""
+    g = np.load(golden_dir / "closures.npz")
+    sim = ds.DiffractionSimulation(g[f"{tag}_coords"], intensities=g[f"{tag}_intensities"],
+                                   calibration=tuple(g[f"{tag}_calibration"]), with_direct_beam=True)
+    got = sim.get_diffraction_pattern(shape=(256, 256), sigma=6, **kw)
+    ref = g[f"{tag}_pattern"]
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= IMG_ATOL
+    with pytest.raises(NotImplementedError):
+        sim.get_diffraction_pattern(shape=(256, 200))
+
+
+@pytest.mark.parametrize("angle", [0, 90, 45])
+def test_knife_edge_pixels_are_decided_without_the_references_ulp_noise(golden_dir, angle):
+    """Spots whose pixel coordinate is an exact integer (here: multiples of 25 px): the reference decides the truncation
+    by the <= 1 ulp noise of r cos(atan2(y, x) + a) + cx (27.999999999999996 -> pixel 27), the kernel's algebraic form does
+    not (28.0 -> pixel 28).  Characterised against the reference golden: every disagreement is a spot on such a knife edge,
+    it moves by exactly one pixel, and the rendered template is the oracle's rasterisation of the kernel's pixel choice."""
+    g = np.load(golden_dir / "closures.npz")
+    coords, inten = g["knife_coords"], g["knife_intensities"]
+    live = np.any(coords, axis=1)                       # with_direct_beam=False masks (0, 0, 0), :171-179
+    ref_px = g[f"knife_pixels_{angle}"]
+    a = np.deg2rad(angle)
+    ca, sa = (1.0, 0.0) if angle == 0 else (np.cos(a), np.sin(a))
+    xs, ys = coords[live, 0] / 0.01, coords[live, 1] / 0.01
+    ours = np.stack([xs * ca - ys * sa + 128, ys * ca + xs * sa + 128], axis=1)
+    assert np.abs(ours - ref_px).max() < 1e-12           # the same numbers up to the reference's round-off ...
+    differ = (ours.astype(int) != ref_px.astype(int)).any(axis=1)
+    assert differ.sum() <= 0.25 * len(ours)              # ... (measured: 8 / 17 / 2 of 80 spots at 0 / 90 / 45 degrees)
+    on_edge = np.abs(ref_px - np.rint(ref_px)).min(axis=1) < 1e-9
+    assert np.all(on_edge[differ])                        # ... and only knife-edge spots can land one pixel apart
+    assert np.abs(ours.astype(int) - ref_px.astype(int)).max() <= 1
+    sim = ds.DiffractionSimulation(coords, intensities=1.0 + np.arange(len(coords)) % 7, calibration=0.01)
+    got = sim.get_diffraction_pattern(shape=(256, 256), sigma=2, in_plane_angle=angle)
+    inside = (ours[:, 0] >= 0) & (ours[:, 0] < 256) & (ours[:, 1] >= 0) & (ours[:, 1] < 256)
+    expect = K.pattern_from_pixel_coordinates_and_intensities(ours[inside].astype(int), inten[inside], (256, 256), 2, 1)
+    expect = expect / expect.max()
+    assert np.abs(got - expect).max() <= IMG_ATOL
+    if not differ.any():
+        assert np.abs(got - g[f"knife_pattern_{angle}"]).max() <= IMG_ATOL
+
+
+def test_objects_exposing_only_the_orix_and_diffpy_attribute_surface():
+    """The drop-in takes orix.Phase / orix.Rotation / diffpy.structure objects by duck typing.  Neither library is in the
+    image, so this feeds minimal objects that expose EXACTLY the attribute surface SURVEY.md section 8b lists (anything
+    else raises AttributeError) through calculate_diffraction2d + get_diffraction_pattern: same result as the stand-ins."""
+    import copy
+
+    class OnlyThese:
+        _allowed = ()
+
+        def __getattr__(self, name):        # only called for names that are not real attributes
+            raise AttributeError(f"{type(self).__name__} does not expose .{name} (not part of the orix / diffpy surface used)")
+
+    class MinLattice(OnlyThese):            # diffpy.structure.Lattice: base, recbase, stdbase, baserot, rnorm, setLatPar, abcABG
+        def __init__(self, lat):
+            self.base, self.recbase = np.array(lat.base), np.array(lat.recbase)
+            self.stdbase, self.baserot = np.array(lat.stdbase), np.array(lat.baserot)
+            self._abc = lat.abcABG()
+
+        def rnorm(self, hkl):
+            return np.sqrt(((np.asarray(hkl, float) @ self.recbase.T) ** 2).sum(axis=-1))
+
+        def abcABG(self):
+            return self._abc
+
+        def setLatPar(self, baserot=None, **kw):
+            assert not kw
+            old = self.baserot
+            self.baserot = np.array(baserot)
+            rot = np.linalg.solve(old, self.baserot)          # base = stdbase @ baserot
+            self.base = self.base @ rot
+            self.recbase = np.linalg.inv(self.base)
+
+    class MinAtom(OnlyThese):               # diffpy.structure.Atom: element, xyz, occupancy
+        def __init__(self, a):
+            self.element, self.xyz, self.occupancy = a.element, np.array(a.xyz), a.occupancy
+
+    class MinStructure(OnlyThese):          # diffpy.structure.Structure: iterable of atoms, .lattice
+        def __init__(self, st):
+            self._atoms = [MinAtom(a) for a in st]
+            self.lattice = MinLattice(st.lattice)
+
+        def __iter__(self):
+            return iter(self._atoms)
+
+        def __len__(self):
+            return len(self._atoms)
+
+    class MinPhase(OnlyThese):              # orix.crystal_map.Phase: name, structure, point_group, deepcopy()
+        def __init__(self, ph):
+            self.name, self.point_group, self.structure = ph.name, ph.point_group, MinStructure(ph.structure)
+
+        def deepcopy(self):
+            return copy.deepcopy(self)
+
+    class MinRotation(OnlyThese):           # orix.quaternion.Rotation: data, size, to_matrix(), ~, iteration / indexing
+        def __init__(self, data):
+            self.data = np.atleast_2d(np.asarray(data, float))
+
+        @property
+        def size(self):
+            return self.data.shape[0]
+
+        @property
+        def shape(self):
+            return (self.data.shape[0],)
+
+        def to_matrix(self):
+            return Rotation(self.data).to_matrix()
+
+        def __invert__(self):
+            q = self.data.copy()
+            q[:, 1:] *= -1
+            return MinRotation(q)
+
+        def __getitem__(self, key):
+            return MinRotation(self.data[key])
+
+        def __iter__(self):
+            return (MinRotation(self.data[i]) for i in range(self.size))
+
+        def __len__(self):
+            return self.size
+
+    phase = cases.phase("ti")               # hexagonal: exercises the a || x, c* || z realignment of the lattice
+    rot = Rotation.random(5, rng=3)
+    gen = ds.SimulationGenerator(300)
+    ref = gen.calculate_diffraction2d(phase, rot, reciprocal_radius=1.5, max_excitation_error=0.02)
+    got = gen.calculate_diffraction2d(MinPhase(phase), MinRotation(rot.data), reciprocal_radius=1.5, max_excitation_error=0.02)
+    for i in range(5):
+        a, b = ref.coordinates[i], got.coordinates[i]
+        np.testing.assert_array_equal(a.hkl, b.hkl)
+        np.testing.assert_array_equal(a.data, b.data)
+        np.testing.assert_array_equal(a.intensity, b.intensity)
+    kw = dict(shape=(128, 128), sigma=4, calibration=1.5 / 64)
+    np.testing.assert_array_equal(ref.get_diffraction_pattern(**kw), got.get_diffraction_pattern(**kw))
+    one = gen.calculate_diffraction2d(MinPhase(phase), MinRotation(rot.data[:1]), reciprocal_radius=1.5)
+    assert one.coordinates.size > 0
