@@ -14,7 +14,7 @@ _LIB_PATH = Path(os.environ.get("DIFFSIMS_B200_LIB") or Path(__file__).resolve()
 _lib = None
 
 # every symbol include/diffsims_b200.h declares
-SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors", "ds_pack_gtable",
+SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors_scratch_bytes", "ds_structure_factors", "ds_pack_gtable",
            "ds_simulate", "ds_render_scratch_bytes", "ds_render_launch_count", "ds_render", "ds_pack_csr", "ds_polar_flatten", "ds_library_pixel_coords",
            "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points", "ds_so3_grid_num_blocks", "ds_so3_grid")
 ABI_VERSION = 2
@@ -41,7 +41,8 @@ def lib():
     if L.ds_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"ABI version {L.ds_abi_version()} != {ABI_VERSION}: rebuild the library")
     P, I, D = c_void_p, c_int32, c_double
-    L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P]
+    L.ds_structure_factors.argtypes = [P, I, P, P, I, P, P, I, P, P, P, I, P, P, P, I, P]
+    L.ds_structure_factors_scratch_bytes.argtypes = [I, I]
     L.ds_pack_gtable.argtypes = [P, I, P, P, P, I, D]
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P, D]
@@ -61,6 +62,7 @@ def lib():
     L.ds_render_launch_count.argtypes = [I, I, I, I, I, D]
     L.ds_render_scratch_bytes.argtypes = [I, I]
     L.ds_render_scratch_bytes.restype = ctypes.c_int64
+    L.ds_structure_factors_scratch_bytes.restype = ctypes.c_int64
     L.ds_beam_grid_num_blocks.restype = ctypes.c_int64
     L.ds_beam_points_num_blocks.restype = ctypes.c_int64
     L.ds_so3_grid_num_blocks.restype = ctypes.c_int64

@@ -9,6 +9,12 @@
 // cancelling terms (|a_i| ~ 200 summing to ~1) and the parity contract is rtol 1e-5 on |F|^2 including
 // weak reflections, which float32 phases/sums cannot meet (hard part 2).  The kernel is
 // therefore bound by the FP64 pipe (sincospi ~ 40 DFMA per atom x g pair), not by HBM or the SFU.
+//
+// Large cells with integer Miller indices (the per-phase g table) take the FACTORISED kernels instead:
+// exp(2 pi i (h x + k y + l z)) = Ex_j[h] Ey_j[k] Ez_j[l], so a small pre-pass tabulates the three phase factors of every
+// atom for h, k, l in [-H, H] (3 N_at (2 H + 1) sincospi in all, the occupancy folded into Ex) and the main kernel needs
+// two complex multiplications per atom x g pair -- 8 DFMA instead of ~40 -- reading table tiles staged in shared memory
+// (lanes of a warp hold consecutive l: Ex / Ey reads are broadcasts, Ez reads are contiguous).
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -102,21 +108,155 @@ structure_factor_kernel(int n_g, const double *__restrict__ hkl, const double *_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// factorised phases (integer hkl, |h|, |k|, |l| <= H)
+// ---------------------------------------------------------------------------------------------------
+constexpr int SFT_THREADS = 256;
+constexpr int SFT_G_PER_THREAD = 3;
+constexpr int SFT_G_TILE = SFT_THREADS * SFT_G_PER_THREAD;
+
+// table[axis][atom][m + H] = (occ_j if axis == 0 else 1) * exp(2 pi i m r_j[axis]),  m = -H .. H
+__global__ void sf_phase_table_kernel(int n_atoms, int H, const double *__restrict__ frac, const double *__restrict__ occ,
+                                      double2 *__restrict__ table) {
+    const int W = 2 * H + 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3ll * n_atoms * W) return;
+    const int m = (int)(idx % W) - H, j = (int)((idx / W) % n_atoms), axis = (int)(idx / ((long long)W * n_atoms));
+    double sn, cs;
+    sincospi(2.0 * (double)m * frac[3 * j + axis], &sn, &cs);
+    const double w = axis == 0 ? occ[j] : 1.0;
+    table[idx] = make_double2(w * cs, w * sn);
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(SFT_THREADS)
+structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const double *__restrict__ gnorm, int n_atoms, int n_elem,
+                            const int *__restrict__ elem_start, const double *__restrict__ coeffs, const double *__restrict__ dw,
+                            const double *__restrict__ prefactor, int H, int atom_tile, const double2 *__restrict__ table,
+                            double *__restrict__ F_out, double *__restrict__ I_out) {
+    extern __shared__ __align__(16) unsigned char sft_smem[];
+    double2 *s_tab = reinterpret_cast<double2 *>(sft_smem);  // [3][atom_tile][W]
+    __shared__ double s_coef[SF_MAX_ELEM * 10];
+    __shared__ double s_dw[SF_MAX_ELEM];
+    __shared__ int s_start[SF_MAX_ELEM + 1];
+    const int W = 2 * H + 1;
+    for (int i = threadIdx.x; i < n_elem * 10; i += SFT_THREADS) s_coef[i] = coeffs[i];
+    for (int i = threadIdx.x; i < n_elem; i += SFT_THREADS) s_dw[i] = dw[i];
+    for (int i = threadIdx.x; i <= n_elem; i += SFT_THREADS) s_start[i] = elem_start[i];
+
+    int ih[SFT_G_PER_THREAD], ik[SFT_G_PER_THREAD], il[SFT_G_PER_THREAD];
+    double g2[SFT_G_PER_THREAD], Fre[SFT_G_PER_THREAD], Fim[SFT_G_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
+        const int g = blockIdx.x * SFT_G_TILE + q * SFT_THREADS + threadIdx.x;
+        ih[q] = ik[q] = il[q] = H;  // (row 0 of the table for the idle threads)
+        g2[q] = 0.0;
+        if (g < n_g) {
+            ih[q] = (int)hkl[3 * g + 0] + H;
+            ik[q] = (int)hkl[3 * g + 1] + H;
+            il[q] = (int)hkl[3 * g + 2] + H;
+            g2[q] = gnorm[g] * gnorm[g];
+        }
+        Fre[q] = Fim[q] = 0.0;
+    }
+    __syncthreads();
+    for (int e = 0; e < n_elem; ++e) {
+        double fe[SFT_G_PER_THREAD], re[SFT_G_PER_THREAD], im[SFT_G_PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
+            // f_e(g^2) * exp(-g^2 B_e / 4): the real part of the reference's complex exponent (:297-301)
+            fe[q] = scattering_factor<MODEL>(g2[q], &s_coef[e * 10]) * exp(-0.25 * g2[q] * s_dw[e]);
+            re[q] = im[q] = 0.0;
+        }
+        for (int base = s_start[e]; base < s_start[e + 1]; base += atom_tile) {
+            const int n_tile = min(atom_tile, s_start[e + 1] - base);
+            __syncthreads();  // the previous tile has been consumed
+            for (int i = threadIdx.x; i < 3 * n_tile * W; i += SFT_THREADS) {
+                const int axis = i / (n_tile * W), rem = i % (n_tile * W);
+                s_tab[(axis * atom_tile) * W + rem] = table[((long long)axis * n_atoms + base) * W + rem];
+            }
+            __syncthreads();
+            const double2 *tx = s_tab, *ty = s_tab + (size_t)atom_tile * W, *tz = s_tab + (size_t)2 * atom_tile * W;
+            for (int j = 0; j < n_tile; ++j) {
+#pragma unroll
+                for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
+                    const double2 a = tx[j * W + ih[q]], b = ty[j * W + ik[q]], c = tz[j * W + il[q]];
+                    const double pr = a.x * b.x - a.y * b.y, pi = a.x * b.y + a.y * b.x;
+                    re[q] += pr * c.x - pi * c.y;
+                    im[q] += pr * c.y + pi * c.x;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
+            Fre[q] = fma(fe[q], re[q], Fre[q]);
+            Fim[q] = fma(fe[q], im[q], Fim[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
+        const int g = blockIdx.x * SFT_G_TILE + q * SFT_THREADS + threadIdx.x;
+        if (g >= n_g) continue;
+        if (F_out) {
+            F_out[2 * g] = Fre[q];
+            F_out[2 * g + 1] = Fim[q];
+        }
+        if (I_out) {
+            const double p = prefactor ? prefactor[g] : 1.0;
+            I_out[g] = p * (Fre[q] * Fre[q] + Fim[q] * Fim[q]);  // sim_utils.py:353
+        }
+    }
+}
+
 }  // namespace ds
+
+extern "C" int64_t ds_structure_factors_scratch_bytes(int32_t n_atoms, int32_t hkl_int_max) {
+    if (n_atoms < 0 || hkl_int_max < 0) return -1;
+    return 3ll * n_atoms * (2ll * hkl_int_max + 1) * 16;
+}
 
 extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl, const double *gnorm,
                                     int32_t n_atoms, const double *frac, const double *occ, int32_t n_elem,
                                     const int32_t *elem_start, const double *coeffs, const double *dw,
                                     int32_t scattering_model, const double *prefactor, double *F_out,
-                                    double *I_out) {
+                                    double *I_out, int32_t hkl_int_max, void *table_scratch) {
     using namespace ds;
     DS_REQUIRE(n_g >= 0 && n_atoms >= 0 && n_elem >= 0, "ds_structure_factors: negative size");
     DS_REQUIRE(n_elem <= SF_MAX_ELEM, "ds_structure_factors: more than %d distinct elements", SF_MAX_ELEM);
     DS_REQUIRE(scattering_model >= 0 && scattering_model <= 2, "ds_structure_factors: unknown scattering model %d",
                scattering_model);
     if (n_g == 0) return 0;
-    const dim3 grid((n_g + SF_THREADS - 1) / SF_THREADS), block(SF_THREADS);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // factorised path: integer indices in a bounded range, a cell large enough to pay for the table pre-pass
+    if (hkl_int_max > 0 && hkl_int_max <= 127 && table_scratch != nullptr && n_atoms >= 32 && n_g >= 4096 &&
+        (reinterpret_cast<uintptr_t>(table_scratch) & 15) == 0) {
+        const int H = hkl_int_max, W = 2 * H + 1;
+        int atom_tile = (int)((64 * 1024) / (3 * W * 16));
+        atom_tile = atom_tile > 64 ? 64 : atom_tile;
+        DS_REQUIRE(atom_tile >= 1, "ds_structure_factors: index range too large for the factorised kernel");
+        double2 *table = static_cast<double2 *>(table_scratch);
+        const long long n_tab = 3ll * n_atoms * W;
+        sf_phase_table_kernel<<<(unsigned)((n_tab + 255) / 256), 256, 0, st>>>(n_atoms, H, frac, occ, table);
+        const size_t smem = (size_t)3 * atom_tile * W * 16;
+        const int grid_t = (n_g + SFT_G_TILE - 1) / SFT_G_TILE;
+#define DS_SFT_LAUNCH(M)                                                                                                   \
+    do {                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                              \
+            cudaFuncSetAttribute(structure_factor_tab_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+        structure_factor_tab_kernel<M><<<grid_t, SFT_THREADS, smem, st>>>(n_g, hkl, gnorm, n_atoms, n_elem, elem_start,    \
+                                                                          coeffs, dw, prefactor, H, atom_tile, table,      \
+                                                                          F_out, I_out);                                   \
+    } while (0)
+        if (scattering_model == DS_SCATT_LOBATO)
+            DS_SFT_LAUNCH(DS_SCATT_LOBATO);
+        else if (scattering_model == DS_SCATT_XTABLES)
+            DS_SFT_LAUNCH(DS_SCATT_XTABLES);
+        else
+            DS_SFT_LAUNCH(DS_SCATT_NONE);
+#undef DS_SFT_LAUNCH
+        return check_launch("ds_structure_factors (factorised)");
+    }
+    const dim3 grid((n_g + SF_THREADS - 1) / SF_THREADS), block(SF_THREADS);
 #define DS_SF_LAUNCH(M)                                                                                       \
     structure_factor_kernel<M><<<grid, block, 0, st>>>(n_g, hkl, gnorm, n_atoms, frac, occ, n_elem, elem_start, \
                                                        coeffs, dw, prefactor, F_out, I_out)

@@ -109,12 +109,14 @@ class AtomTable:
         self.model = SCATTERING_IDS[scattering_params]
 
 
-def launch_structure_factors(atoms: AtomTable, hkl_d, gnorm_d, prefactor_d=None, F=None, I=None):
-    """Enqueue K1 on the current stream (no host work, no synchronisation)."""
+def launch_structure_factors(atoms: AtomTable, hkl_d, gnorm_d, prefactor_d=None, F=None, I=None, hkl_int_max=0,
+                             scratch=None):
+    """Enqueue K1 on the current stream (no host work, no synchronisation).  ``hkl_int_max`` > 0 (all indices are
+    integers of at most that magnitude) with a ``scratch`` tensor lets large cells take the factorised kernels."""
     rc = _cabi.lib().ds_structure_factors(
         _stream(), hkl_d.shape[0], _cabi.ptr(hkl_d), _cabi.ptr(gnorm_d), atoms.n_atoms, _cabi.ptr(atoms.frac),
         _cabi.ptr(atoms.occ), atoms.n_elem, _cabi.ptr(atoms.start), _cabi.ptr(atoms.coeffs), _cabi.ptr(atoms.dw),
-        atoms.model, _cabi.ptr(prefactor_d), _cabi.ptr(F), _cabi.ptr(I))
+        atoms.model, _cabi.ptr(prefactor_d), _cabi.ptr(F), _cabi.ptr(I), int(hkl_int_max), _cabi.ptr(scratch))
     _cabi.check(rc, "ds_structure_factors")
 
 
@@ -206,6 +208,12 @@ class GTablePlan:
         gnorm = np.sqrt((self.xyz_host ** 2).sum(axis=1))
         self.g_max = float(gnorm.max()) if gnorm.size else 0.0
         self.hkl_d = torch.as_tensor(self.hkl.astype(float), device=dev)
+        # integer Miller indices of bounded magnitude: K1 may factorise the phases (large cells)
+        self.hkl_int_max = int(np.abs(self.hkl).max()) if self.hkl.size and np.issubdtype(self.hkl.dtype, np.integer) else 0
+        self.sf_scratch = None
+        if 0 < self.hkl_int_max <= 127 and self.atoms.n_atoms >= 32:
+            nb = int(_cabi.lib().ds_structure_factors_scratch_bytes(self.atoms.n_atoms, self.hkl_int_max))
+            self.sf_scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
         self.gnorm_d = torch.as_tensor(gnorm, device=dev)
         self.xyz_d = torch.as_tensor(self.xyz_host, device=dev)
         self.lines = None
@@ -252,7 +260,9 @@ class GTablePlan:
         f32 = torch.empty((n, 4), dtype=torch.float32, device=dev)
         mark = bool(n) and extinct_rel_cut > 0.0 and not np.any(self.hkl[-1])   # last row = (000)
         if n:
-            launch_structure_factors(self.atoms, self.hkl_d, self.gnorm_d, None, None, I0)
+            launch_structure_factors(self.atoms, self.hkl_d, self.gnorm_d, None, None, I0,
+                                     hkl_int_max=self.hkl_int_max if self.sf_scratch is not None else 0,
+                                     scratch=self.sf_scratch)
             _cabi.check(_cabi.lib().ds_pack_gtable(_stream(), n, _cabi.ptr(self.xyz_d), _cabi.ptr(f32),
                                                    _cabi.ptr(I0) if mark else None, n - 1 if mark else -1,
                                                    float(extinct_rel_cut) if mark else 0.0), "ds_pack_gtable")

@@ -81,7 +81,12 @@ int ds_get_option(const char *name, int32_t *value);
  * inv(stdbase @ recbase) (sim_utils.py:290-291; a 3x3 host-side matmul).
  * Outputs (either may be NULL): F_out[n_g][2] = (re, im); I_out[n_g] =
  * prefactor[g] * |F|^2 (prefactor NULL = 1).
+ * hkl_int_max > 0 is the caller's promise that every entry of hkl is an integer with |.| <= hkl_int_max (<= 127): with
+ * a scratch buffer of ds_structure_factors_scratch_bytes(n_atoms, hkl_int_max) bytes (16-byte aligned) large cells then
+ * take the factorised kernels (per-atom phase tables Ex[h] Ey[k] Ez[l], two complex multiplications per atom x g pair
+ * instead of a sincospi).  hkl_int_max = 0 / table_scratch = NULL: the direct evaluation (any real hkl).
  */
+int64_t ds_structure_factors_scratch_bytes(int32_t n_atoms, int32_t hkl_int_max);
 int ds_structure_factors(void *stream,
                          int32_t n_g, const double *hkl /*[n_g][3]*/, const double *gnorm /*[n_g]*/,
                          int32_t n_atoms, const double *frac /*[n_atoms][3]*/, const double *occ /*[n_atoms]*/,
@@ -89,7 +94,8 @@ int ds_structure_factors(void *stream,
                          const double *coeffs /*[n_elem][5][2] (a_i, b_i)*/, const double *dw /*[n_elem]*/,
                          int32_t scattering_model,
                          const double *prefactor /*[n_g] or NULL*/,
-                         double *F_out /*[n_g][2] or NULL*/, double *I_out /*[n_g] or NULL*/);
+                         double *F_out /*[n_g][2] or NULL*/, double *I_out /*[n_g] or NULL*/,
+                         int32_t hkl_int_max, void *table_scratch /* or NULL */);
 
 /*
  * Pack the per-phase g table for K2: out[g] = (gx, gy, gz, |g|^2) as float (16-byte rows,
