@@ -550,6 +550,10 @@ def main():
     elapsed_ms = max_over_ranks(t0.elapsed_time(t1))
     launches = launches_per_step * args.steps
     k_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in k_events.items()}
+    # K1 / K2 are tens of microseconds: inside the eager step loop their event intervals also hold the host's launch gaps,
+    # so they are timed on their own (median of back-to-back launches); K3's interval (>= 1 ms) is taken from the loop
+    k_ms["k1"] = _time_ms(lambda: builder.prepare())
+    k_ms["k2"] = _time_ms(lambda: builder.simulate(q_dev))
     builder.assert_no_overflow(spots)           # the unchecked timed passes stayed inside the calibrated capacity
     mean_spots = float(gather_counts(spots.count).float().mean().item())
     value = world * B * args.steps / (elapsed_ms * 1e-3)

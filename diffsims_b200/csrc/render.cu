@@ -158,10 +158,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
             for (int e = gtid; e < p.table_size; e += GT) fs.hash[e] = 0ull;
             group_sync<G>(group);
             for (int j = gtid; j < n; j += GT) {
-                const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
-                // r cos(+-atan2(y, x) + a) + cx written without the polar round trip
-                const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-                const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+                double px, py;
+                project_spot(p, sxyz[3 * j], sxyz[3 * j + 1], px, py);
                 int key = -1;
                 if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
                     key = (int)py * p.W + (int)px;  // astype(int): truncation
@@ -219,9 +217,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_kernel(const RenderParam
                     bool live = false, inframe = false;
                     double px = 0, py = 0, I = 0, rad = 0;
                     if (j < n) {
-                        const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
-                        px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-                        py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+                        project_spot(p, sxyz[3 * j], sxyz[3 * j + 1], px, py);
                         I = sint[j];
                         // get_diffraction_pattern keeps the in-frame spots only (simulation2d.py:422-430); the bare
                         // rasteriser also spreads spots lying outside the frame into it

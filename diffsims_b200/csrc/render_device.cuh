@@ -48,6 +48,17 @@ struct RenderParams {
     double mean_spots_hint;  // caller's estimate of the mean reflections per template (<= 0: unknown)
 };
 
+// Detector pixel coordinates of a spot (simulation2d.py:261-285: r cos(+-atan2(y, x) + a) + cx, written without the polar
+// round trip).  Every operation is individually rounded IEEE double arithmetic in this fixed order -- no fused
+// multiply-add -- so the pixel a coordinate truncates to is exactly what evaluating
+//     px = (x / cal) * cos(a) - (m * (y / cal)) * sin(a) + cx,   py = (m * (y / cal)) * cos(a) + (x / cal) * sin(a) + cy
+// in numpy gives, on every kernel and every compiler version (knife-edge pixels are decided reproducibly).
+__device__ __forceinline__ void project_spot(const RenderParams &p, double x, double y, double &px, double &py) {
+    const double xs = __ddiv_rn(x, p.cal), ys = __dmul_rn(p.mirror, __ddiv_rn(y, p.cal));
+    px = __dadd_rn(__dsub_rn(__dmul_rn(xs, p.ca), __dmul_rn(ys, p.sa)), p.cx);
+    py = __dadd_rn(__dadd_rn(__dmul_rn(ys, p.ca), __dmul_rn(xs, p.sa)), p.cy);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // shared-memory carve-up helpers
 // ---------------------------------------------------------------------------------------------------

@@ -144,9 +144,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             for (int e = lane; e < p.table_size; e += 32) hash[e] = 0ull;
             __syncwarp();
             for (int j = lane; j < n; j += 32) {
-                const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
-                const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-                const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+                double px, py;
+                project_spot(p, sxyz[3 * j], sxyz[3 * j + 1], px, py);
                 int kk = -1;
                 if (px >= 0.0 && px < (double)p.W && py >= 0.0 && py < (double)p.H) {
                     kk = (int)py * p.W + (int)px;

@@ -37,10 +37,8 @@ __global__ void __launch_bounds__(256) render_prepare_kernel(const RenderParams 
         uint2 *gspot = reinterpret_cast<uint2 *>(rec + 32);
         unsigned short *glist = reinterpret_cast<unsigned short *>(rec + 32 + (size_t)p.cap * 8);
         auto project = [&](int j) -> unsigned {  // astype(int) truncates
-            const double xs = sxyz[3 * j] / p.cal, ys = sxyz[3 * j + 1] / p.cal;
-            // r cos(+-atan2(y, x) + a) + cx written without the polar round trip
-            const double px = xs * p.ca - p.mirror * ys * p.sa + p.cx;
-            const double py = p.mirror * ys * p.ca + xs * p.sa + p.cy;
+            double px, py;
+            project_spot(p, sxyz[3 * j], sxyz[3 * j + 1], px, py);
             if (px >= 0.0 && px < (double)W && py >= 0.0 && py < (double)H) return (unsigned)(int)px | ((unsigned)(int)py << 16);
             return 0xffffffffu;
         };

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
     // (in scan-line mode the host passes tile_g = bytes of the line tables / 16, n_tiles = 1)
     double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1));
     if (GENERAL)
-        for (int j = threadIdx.x; j < p.n_quad; j += SIM_THREADS) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
+        for (int j = threadIdx.x; j < p.n_quad; j += blockDim.x) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_list[SIM_WARPS][64];
 
@@ -245,9 +245,11 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
     const uint32_t tile_base_s = smem_u32(smem_raw);
     int local_max_count = 0;
 
-    const int n_batches = (p.n_rot + SIM_WARPS - 1) / SIM_WARPS;
+    // rotations per CTA = warps per CTA: 8 normally, fewer when the launch has too few rotations to fill the SMs
+    const int wpb = blockDim.x >> 5;
+    const int n_batches = (p.n_rot + wpb - 1) / wpb;
     for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-        const int rot = batch * SIM_WARPS + warp;
+        const int rot = batch * wpb + warp;
         const bool active = rot < p.n_rot;
         WarpState w;
         w.n_out = 0;
@@ -597,7 +599,17 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         shape_model != DS_SHAPE_NONE_RETURN_S && shape_model != DS_SHAPE_BINARY)
         p.n_quad = (shape_model == DS_SHAPE_LORENTZIAN || shape_model == DS_SHAPE_ATANC) ? 2048 : 8192;
     const size_t smem = (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1) + (size_t)p.n_quad * 8;
-    const int n_batches = (n_rot + SIM_WARPS - 1) / SIM_WARPS;
+    // Few rotations over a large table (one warp per rotation cannot fill 148 SMs): smaller CTAs spread the rotations
+    // over more SMs; the table is then streamed by more CTAs, which L2 absorbs.  sim_split = 1 / 2 / 4 / 8 forces the
+    // warps per CTA.
+    int wpb = SIM_WARPS;
+    while (wpb > 1 && (n_rot + wpb - 1) / wpb < 2 * num_sms()) wpb >>= 1;
+    if (n_g < 2048) wpb = SIM_WARPS;  // small tables: the launch is latency-bound either way
+    {
+        const int o = option(OPT_SIM_SPLIT);
+        if (o == 1 || o == 2 || o == 4 || o == 8) wpb = o;
+    }
+    const int n_batches = (n_rot + wpb - 1) / wpb;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // no precession: one lean kernel per shape factor model; anything with precession: the general kernel
     auto launch = [&](auto kern, int slot) {
@@ -605,10 +617,10 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SIM_TILE_G * 16 + 8192 * 8);
         int blocks_per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SIM_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpb * 32, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         const int grid = n_batches < num_sms() * blocks_per_sm ? n_batches : num_sms() * blocks_per_sm;
-        kern<<<grid, SIM_THREADS, smem, st>>>(p, n_tiles, tile_g);
+        kern<<<grid, wpb * 32, smem, st>>>(p, n_tiles, tile_g);
     };
 #define DS_SIM(M, SLOT)                                   \
     do {                                                  \

@@ -132,34 +132,57 @@ template <int MODEL>
 __global__ void __launch_bounds__(SFT_THREADS)
 structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const double *__restrict__ gnorm, int n_atoms, int n_elem,
                             const int *__restrict__ elem_start, const double *__restrict__ coeffs, const double *__restrict__ dw,
-                            const double *__restrict__ prefactor, int H, int atom_tile, const double2 *__restrict__ table,
+                            const double *__restrict__ prefactor, int H, int smem_entries, const double2 *__restrict__ table,
                             double *__restrict__ F_out, double *__restrict__ I_out) {
     extern __shared__ __align__(16) unsigned char sft_smem[];
-    double2 *s_tab = reinterpret_cast<double2 *>(sft_smem);  // [3][atom_tile][W]
+    double2 *s_tab = reinterpret_cast<double2 *>(sft_smem);  // [atom_tile][Wh + Wk + Wl]: Ex | Ey | Ez of an atom
     __shared__ double s_coef[SF_MAX_ELEM * 10];
     __shared__ double s_dw[SF_MAX_ELEM];
     __shared__ int s_start[SF_MAX_ELEM + 1];
+    __shared__ int s_lo[3], s_hi[3];
     const int W = 2 * H + 1;
     for (int i = threadIdx.x; i < n_elem * 10; i += SFT_THREADS) s_coef[i] = coeffs[i];
     for (int i = threadIdx.x; i < n_elem; i += SFT_THREADS) s_dw[i] = dw[i];
     for (int i = threadIdx.x; i <= n_elem; i += SFT_THREADS) s_start[i] = elem_start[i];
+    if (threadIdx.x < 3) {
+        s_lo[threadIdx.x] = 1 << 20;
+        s_hi[threadIdx.x] = -(1 << 20);
+    }
+    __syncthreads();
 
+    // this CTA's g vectors (consecutive table rows: l runs fastest, so h and k span a few values only) and the index
+    // ranges its table tiles need
     int ih[SFT_G_PER_THREAD], ik[SFT_G_PER_THREAD], il[SFT_G_PER_THREAD];
     double g2[SFT_G_PER_THREAD], Fre[SFT_G_PER_THREAD], Fim[SFT_G_PER_THREAD];
+    bool live[SFT_G_PER_THREAD];
 #pragma unroll
     for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
         const int g = blockIdx.x * SFT_G_TILE + q * SFT_THREADS + threadIdx.x;
-        ih[q] = ik[q] = il[q] = H;  // (row 0 of the table for the idle threads)
+        live[q] = g < n_g;
+        ih[q] = ik[q] = il[q] = 0;
         g2[q] = 0.0;
-        if (g < n_g) {
-            ih[q] = (int)hkl[3 * g + 0] + H;
-            ik[q] = (int)hkl[3 * g + 1] + H;
-            il[q] = (int)hkl[3 * g + 2] + H;
+        if (live[q]) {
+            ih[q] = (int)hkl[3 * g + 0];
+            ik[q] = (int)hkl[3 * g + 1];
+            il[q] = (int)hkl[3 * g + 2];
             g2[q] = gnorm[g] * gnorm[g];
+            atomicMin(&s_lo[0], ih[q]), atomicMax(&s_hi[0], ih[q]);
+            atomicMin(&s_lo[1], ik[q]), atomicMax(&s_hi[1], ik[q]);
+            atomicMin(&s_lo[2], il[q]), atomicMax(&s_hi[2], il[q]);
         }
         Fre[q] = Fim[q] = 0.0;
     }
     __syncthreads();
+    const int h0 = s_lo[0], k0 = s_lo[1], l0 = s_lo[2];
+    const int Wh = s_hi[0] - h0 + 1, Wk = s_hi[1] - k0 + 1, Wl = s_hi[2] - l0 + 1;
+    const int rows = Wh + Wk + Wl;
+    const int atom_tile = max(1, min(128, smem_entries / rows));  // (rows <= 3 (2 H + 1) <= smem_entries: at least one atom)
+#pragma unroll
+    for (int q = 0; q < SFT_G_PER_THREAD; ++q) {  // offsets inside an atom's smem row (idle threads read entry 0)
+        ih[q] = live[q] ? ih[q] - h0 : 0;
+        ik[q] = live[q] ? Wh + ik[q] - k0 : 0;
+        il[q] = live[q] ? Wh + Wk + il[q] - l0 : 0;
+    }
     for (int e = 0; e < n_elem; ++e) {
         double fe[SFT_G_PER_THREAD], re[SFT_G_PER_THREAD], im[SFT_G_PER_THREAD];
 #pragma unroll
@@ -171,16 +194,19 @@ structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const doubl
         for (int base = s_start[e]; base < s_start[e + 1]; base += atom_tile) {
             const int n_tile = min(atom_tile, s_start[e + 1] - base);
             __syncthreads();  // the previous tile has been consumed
-            for (int i = threadIdx.x; i < 3 * n_tile * W; i += SFT_THREADS) {
-                const int axis = i / (n_tile * W), rem = i % (n_tile * W);
-                s_tab[(axis * atom_tile) * W + rem] = table[((long long)axis * n_atoms + base) * W + rem];
+            for (int i = threadIdx.x; i < n_tile * rows; i += SFT_THREADS) {
+                const int j = i / rows, r = i % rows;
+                // row r of an atom: Ex[h0 + r] | Ey[k0 + r - Wh] | Ez[l0 + r - Wh - Wk]
+                const int axis = r < Wh ? 0 : (r < Wh + Wk ? 1 : 2);
+                const int m = axis == 0 ? h0 + r : (axis == 1 ? k0 + r - Wh : l0 + r - Wh - Wk);
+                s_tab[i] = table[((long long)axis * n_atoms + base + j) * W + m + H];
             }
             __syncthreads();
-            const double2 *tx = s_tab, *ty = s_tab + (size_t)atom_tile * W, *tz = s_tab + (size_t)2 * atom_tile * W;
             for (int j = 0; j < n_tile; ++j) {
+                const double2 *row = s_tab + (size_t)j * rows;
 #pragma unroll
                 for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
-                    const double2 a = tx[j * W + ih[q]], b = ty[j * W + ik[q]], c = tz[j * W + il[q]];
+                    const double2 a = row[ih[q]], b = row[ik[q]], c = row[il[q]];
                     const double pr = a.x * b.x - a.y * b.y, pi = a.x * b.y + a.y * b.x;
                     re[q] += pr * c.x - pi * c.y;
                     im[q] += pr * c.y + pi * c.x;
@@ -196,7 +222,7 @@ structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const doubl
 #pragma unroll
     for (int q = 0; q < SFT_G_PER_THREAD; ++q) {
         const int g = blockIdx.x * SFT_G_TILE + q * SFT_THREADS + threadIdx.x;
-        if (g >= n_g) continue;
+        if (!live[q]) continue;
         if (F_out) {
             F_out[2 * g] = Fre[q];
             F_out[2 * g + 1] = Fim[q];
@@ -231,20 +257,18 @@ extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl
     if (hkl_int_max > 0 && hkl_int_max <= 127 && table_scratch != nullptr && n_atoms >= 32 && n_g >= 4096 &&
         (reinterpret_cast<uintptr_t>(table_scratch) & 15) == 0) {
         const int H = hkl_int_max, W = 2 * H + 1;
-        int atom_tile = (int)((64 * 1024) / (3 * W * 16));
-        atom_tile = atom_tile > 64 ? 64 : atom_tile;
-        DS_REQUIRE(atom_tile >= 1, "ds_structure_factors: index range too large for the factorised kernel");
+        const size_t smem = 64 * 1024;
+        const int smem_entries = (int)(smem / 16);  // >= 3 W for H <= 127
         double2 *table = static_cast<double2 *>(table_scratch);
         const long long n_tab = 3ll * n_atoms * W;
         sf_phase_table_kernel<<<(unsigned)((n_tab + 255) / 256), 256, 0, st>>>(n_atoms, H, frac, occ, table);
-        const size_t smem = (size_t)3 * atom_tile * W * 16;
         const int grid_t = (n_g + SFT_G_TILE - 1) / SFT_G_TILE;
 #define DS_SFT_LAUNCH(M)                                                                                                   \
     do {                                                                                                                   \
         if (smem > 48 * 1024)                                                                                              \
             cudaFuncSetAttribute(structure_factor_tab_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
         structure_factor_tab_kernel<M><<<grid_t, SFT_THREADS, smem, st>>>(n_g, hkl, gnorm, n_atoms, n_elem, elem_start,    \
-                                                                          coeffs, dw, prefactor, H, atom_tile, table,      \
+                                                                          coeffs, dw, prefactor, H, smem_entries, table,   \
                                                                           F_out, I_out);                                   \
     } while (0)
         if (scattering_model == DS_SCATT_LOBATO)

@@ -2,9 +2,11 @@
 (diffsims/generators/library_generator.py:36-152), B200-native: one K2 launch per phase instead of a
 Python loop over orientations.  ``VectorLibraryGenerator`` is a different algorithm and out of scope."""
 import numpy as np
+import torch
 
 from .. import engine
-from ..libraries.diffraction_library import DiffractionLibrary
+from ..library import pack_csr
+from ..libraries.diffraction_library import DiffractionLibrary, LazyObjectArray
 from ..sims.diffraction_simulation import DiffractionSimulation
 
 __all__ = ["DiffractionLibraryGenerator"]
@@ -29,26 +31,36 @@ class DiffractionLibraryGenerator:
             gt, spots = diffractor.calculate_ed_data_batch(
                 structure, reciprocal_radius, orientations, max_excitation_error, shape_factor_width,
                 debye_waller_factors)
-            pix = engine.library_pixel_coords(spots.count, spots.xyz, calibration, half_shape).cpu().numpy()
-            count = spots.count.cpu().numpy()
-            xyz = spots.xyz.cpu().numpy()
-            inten = spots.intensity.cpu().numpy()
-            gidx = spots.g_index.cpu().numpy()
+            # padded rows -> CSR on the device (ds_pack_csr), pixel coordinates of the packed rows (:129-132,
+            # ds_library_pixel_coords over the packed list as one long row), one compact device->host copy; the
+            # per-orientation objects are made lazily (a 3e5-orientation library costs no Python loop here)
+            packed = pack_csr(spots)
+            total = packed.g_index.shape[0]
+            pix = engine.library_pixel_coords(torch.tensor([total], dtype=torch.int32, device=packed.xyz.device),
+                                              packed.xyz.reshape(1, max(total, 1), 3) if total else packed.xyz.reshape(1, 0, 3),
+                                              calibration, half_shape).reshape(-1, 2).cpu().numpy() if total else \
+                np.zeros((0, 2), dtype=np.int32)
+            off = packed.offsets.cpu().numpy()
+            xyz = packed.xyz.cpu().numpy()
+            inten = packed.intensity.cpu().numpy()
+            hkl = gt.hkl[packed.g_index.cpu().numpy()]
 
-            simulations = np.empty(num_orientations, dtype="object")
-            pixel_coords = np.empty(num_orientations, dtype="object")
-            intensities = np.empty(num_orientations, dtype="object")
-            for i in range(num_orientations):
-                n = count[i]
-                simulation = DiffractionSimulation(
-                    coordinates=xyz[i, :n].copy(), indices=gt.hkl[gidx[i, :n]], intensities=inten[i, :n].copy(),
-                    with_direct_beam=with_direct_beam)
-                simulation.calibration = calibration
-                simulations[i] = simulation
-                # :129-132, computed for the whole library by ds_library_pixel_coords; the direct-beam mask of
-                # the container (with_direct_beam=False hides the (000) row) applies to the pixel list as well
-                pixel_coords[i] = pix[i, :n][simulation.direct_beam_mask].astype(int)
-                intensities[i] = simulation.intensities
+            def make_simulation(i, off=off, xyz=xyz, inten=inten, hkl=hkl):
+                lo, hi = off[i], off[i + 1]
+                sim = DiffractionSimulation(coordinates=xyz[lo:hi].copy(), indices=hkl[lo:hi], intensities=inten[lo:hi].copy(),
+                                            with_direct_beam=with_direct_beam)
+                sim.calibration = calibration
+                return sim
+
+            simulations = LazyObjectArray(num_orientations, make_simulation)
+            # the direct-beam mask of the container (with_direct_beam=False hides the (000) row, sims/...:171-179) applies to
+            # the pixel and intensity lists as well
+            mask_of = (lambda lo, hi, xyz=xyz: np.ones(hi - lo, dtype=bool)) if with_direct_beam else \
+                (lambda lo, hi, xyz=xyz: np.any(xyz[lo:hi], axis=1))
+            pixel_coords = LazyObjectArray(num_orientations, lambda i, off=off, pix=pix, m=mask_of:
+                                           pix[off[i]:off[i + 1]][m(off[i], off[i + 1])].astype(int))
+            intensities = LazyObjectArray(num_orientations, lambda i, off=off, inten=inten, m=mask_of:
+                                          inten[off[i]:off[i + 1]][m(off[i], off[i + 1])].copy())
 
             diffraction_library[phase_name] = {
                 "simulations": simulations,

@@ -9,7 +9,7 @@ import pickle
 
 import numpy as np
 
-__all__ = ["DiffractionLibrary", "load_DiffractionLibrary"]
+__all__ = ["DiffractionLibrary", "load_DiffractionLibrary", "LazyObjectArray"]
 
 _ANGLE_TOLERANCE = 1e-2  # summed |delta Euler| below which an orientation counts as found (reference :62)
 
@@ -29,6 +29,66 @@ def _get_library_entry_from_angles(library, phase, angles):
         if np.abs(np.asarray(euler, dtype=float) - target).sum() < _ANGLE_TOLERANCE:
             return index
     raise ValueError("It appears that no library entry lies with 1e-2 of the target angle")
+
+
+def _as_object_array(items):
+    out = np.empty(len(items), dtype="object")
+    for i, it in enumerate(items):
+        out[i] = it
+    return out
+
+
+class LazyObjectArray:
+    """Stand-in for the reference's 1-D numpy object arrays (``simulations`` / ``pixel_coords`` / ``intensities``) over
+    the packed result of a batched build: entry ``i`` is made by ``make(i)`` when it is first asked for, so a library
+    of 3e5 orientations costs no per-orientation Python work until it is looked at.  Indexing with an integer returns
+    the entry, with a slice / index array a real object array; ``np.asarray`` and pickling materialise everything."""
+
+    dtype = np.dtype("object")
+    ndim = 1
+
+    def __init__(self, n, make):
+        self._n, self._make, self._cache = int(n), make, {}
+
+    def __len__(self):
+        return self._n
+
+    @property
+    def shape(self):
+        return (self._n,)
+
+    @property
+    def size(self):
+        return self._n
+
+    def _one(self, i):
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(f"index {i} is out of bounds for axis 0 with size {self._n}")
+        if i not in self._cache:
+            self._cache[i] = self._make(i)
+        return self._cache[i]
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self._one(key)
+        if isinstance(key, slice):
+            return _as_object_array([self._one(i) for i in range(*key.indices(self._n))])
+        idx = np.asarray(key)
+        if idx.dtype == bool:
+            idx = np.nonzero(idx)[0]
+        return _as_object_array([self._one(i) for i in idx.reshape(-1)])
+
+    def __iter__(self):
+        return (self._one(i) for i in range(self._n))
+
+    def __array__(self, dtype=None, copy=None):
+        return _as_object_array(list(self))
+
+    def __reduce__(self):           # pickles as the plain object array the reference stores
+        return (_as_object_array, (list(self),))
 
 
 class DiffractionLibrary(dict):

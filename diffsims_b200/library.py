@@ -275,39 +275,64 @@ class TemplateLibraryBuilder:
         self.check_capacity()     # synchronises; a truncated build raises instead of returning
         return h2d, d2h
 
-    def run_host_spots(self, quats_host, chunk=65536, polar=False):
-        """HOST rotations in, packed spot lists on the HOST out: ``PackedSpots`` with pinned tensors (and, with
-        ``polar=True``, the padded (r, theta, intensity) arrays of polar_flatten_simulations).  K1 -> K2 -> CSR pack ->
-        device->host copy of ~40 bytes per reflection; no image is rendered.  Returns (packed, h2d_bytes, d2h_bytes)
-        or (packed, polar_arrays, h2d_bytes, d2h_bytes)."""
+    def run_host_spots(self, quats_host, chunk=131072, polar=False):
+        """HOST rotations in, packed spot lists on the HOST out: ``PackedSpots`` in pinned memory (and, with
+        ``polar=True``, the padded (r, theta, intensity) arrays of polar_flatten_simulations, one triple per chunk).
+        K1 -> K2 -> CSR pack -> device->host copy of ~40 bytes per reflection; no image is rendered.  One host
+        synchronisation per chunk (the row total and the capacity check travel together); a chunk that outgrew the
+        row capacity is redone with a larger one.  The pinned result buffers belong to the builder and are reused by
+        the next call.  Returns (packed, h2d_bytes, d2h_bytes) or (packed, polar_arrays, h2d_bytes, d2h_bytes)."""
         dev = engine.device()
         n = quats_host.shape[0]
         self.prepare()
         parts, polar_parts = [], []
         h2d = d2h = 0
-        for lo in range(0, n, chunk):
+        pool = self.__dict__.setdefault("_pinned_pool", {})
+
+        def pinned(key, shape, dtype):
+            need = int(np.prod(shape))
+            t = pool.get(key)
+            if t is None or t.numel() < need or t.dtype != dtype:
+                t = pool[key] = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+            return t[:need].view(shape)
+
+        word = pinned("word", (3,), torch.int64)
+        for ci, lo in enumerate(range(0, n, chunk)):
             hi = min(lo + chunk, n)
             q = quats_host[lo:hi].to(dev, non_blocking=True)
-            spots = self.simulate(q, check_overflow=True)     # (synchronises once per chunk; retries on overflow)
-            packed = pack_csr(spots)
+            while True:
+                spots = self.simulate(q)                      # unchecked launch; verified with the row total below
+                offsets = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(spots.count.clamp(max=spots.cap), 0, out=offsets[1:])
+                stat = torch.stack([offsets[-1], spots.max_count[0].to(torch.int64), spots.count.max().to(torch.int64)])
+                word.copy_(stat, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                total, need, longest = (int(v) for v in word)
+                if need <= spots.cap:
+                    break
+                self.cap = (need + 31) // 32 * 32             # a denser orientation than the capacity allowed: redo
+            g = torch.empty(total, dtype=torch.int32, device=dev)
+            xyz = torch.empty((total, 3), dtype=torch.float64, device=dev)
+            inten = torch.empty(total, dtype=torch.float64, device=dev)
+            _cabi.check(_cabi.lib().ds_pack_csr(engine._stream(), hi - lo, spots.cap, _cabi.ptr(spots.count), _cabi.ptr(offsets),
+                                                _cabi.ptr(spots.g_index), _cabi.ptr(spots.xyz), _cabi.ptr(spots.intensity),
+                                                _cabi.ptr(g), _cabi.ptr(xyz), _cabi.ptr(inten)), "ds_pack_csr")
             self.launches += 1
-            host = PackedSpots(*(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
-                                 (packed.offsets, packed.g_index, packed.xyz, packed.intensity)))
-            for d, s in zip((host.offsets, host.g_index, host.xyz, host.intensity),
-                            (packed.offsets, packed.g_index, packed.xyz, packed.intensity)):
-                d.copy_(s, non_blocking=True)
+            host = PackedSpots(pinned(("off", ci), offsets.shape, torch.int64), pinned(("g", ci), g.shape, torch.int32),
+                               pinned(("xyz", ci), xyz.shape, torch.float64), pinned(("I", ci), inten.shape, torch.float64))
+            for d, s_ in zip((host.offsets, host.g_index, host.xyz, host.intensity), (offsets, g, xyz, inten)):
+                d.copy_(s_, non_blocking=True)
             parts.append(host)
+            d2h += host.nbytes() + 24
             if polar:
-                m = int(spots.count.max().item()) if hi > lo else 0
-                r, t, i = engine.polar_flatten(spots.count, spots.xyz, spots.intensity, max(m, 1))
+                r, t, i = engine.polar_flatten(spots.count, spots.xyz, spots.intensity, max(longest, 1))
                 self.launches += 1
-                hp = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (r, t, i)]
-                for d, s in zip(hp, (r, t, i)):
-                    d.copy_(s, non_blocking=True)
+                hp = [pinned((nm, ci), x.shape, x.dtype) for nm, x in zip(("pr", "pt", "pi"), (r, t, i))]
+                for d, s_ in zip(hp, (r, t, i)):
+                    d.copy_(s_, non_blocking=True)
                 polar_parts.append(hp)
                 d2h += sum(x.numel() * 8 for x in hp)
             h2d += (hi - lo) * 32
-            d2h += packed.nbytes()
         torch.cuda.current_stream().synchronize()
         packed = concat_packed(parts)
         if polar:

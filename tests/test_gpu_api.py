@@ -654,7 +654,7 @@ def test_knife_edge_pixels_are_decided_without_the_references_ulp_noise(golden_d
     a = np.deg2rad(angle)
     ca, sa = (1.0, 0.0) if angle == 0 else (np.cos(a), np.sin(a))
     xs, ys = coords[live, 0] / 0.01, coords[live, 1] / 0.01
-    ours = np.stack([xs * ca - ys * sa + 128, ys * ca + xs * sa + 128], axis=1)
+    ours = np.stack([(xs * ca - ys * sa) + 128, (ys * ca + xs * sa) + 128], axis=1)   # the kernels' documented rule (no FMA)
     assert np.abs(ours - ref_px).max() < 1e-12           # the same numbers up to the reference's round-off ...
     differ = (ours.astype(int) != ref_px.astype(int)).any(axis=1)
     assert differ.sum() <= 0.25 * len(ours)              # ... (measured: 8 / 17 / 2 of 80 spots at 0 / 90 / 45 degrees)
