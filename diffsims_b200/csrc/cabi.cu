@@ -34,6 +34,7 @@ static const OptDef g_defs[OPT_COUNT] = {
     {"render_mma_tmpl_min", "DS_RENDER_MMA_TMPL_MIN"},
     {"render_umma", "DS_RENDER_UMMA"},
     {"render_umma_window", "DS_RENDER_UMMA_WINDOW"},
+    {"render_zero_tma", "DS_RENDER_ZERO_TMA"},
     {"sim_lines", "DS_SIM_LINES"},
     {"sim_split", "DS_SIM_SPLIT"},
 };

@@ -24,6 +24,7 @@ enum Opt {
     OPT_RENDER_MMA_TMPL_MIN,
     OPT_RENDER_UMMA,
     OPT_RENDER_UMMA_WINDOW,
+    OPT_RENDER_ZERO_TMA,
     OPT_SIM_LINES,
     OPT_SIM_SPLIT,
     OPT_COUNT

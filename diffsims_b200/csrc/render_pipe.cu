@@ -15,9 +15,13 @@
 // Two slots per front warp, so stores of template k overlap the whole preparation of template k+1.
 // DENSE instantiations carry the tensor-core path of accumulate_region (render_device.cuh) for libraries with
 // hundreds of reflections per template; sparse libraries run the lean ones.
+#include <cuda.h>  // CUtensorMap (type only)
+
 #include "render_device.cuh"
 
 namespace ds {
+
+int make_image_tensor_map(CUtensorMap *tmap, float *images, int n_tmpl, int H, int W, int box_w, int box_h, bool swizzle128);
 
 // NF front warps (1 for the sparsest patterns, 2 when the preparation of a template is heavier) feed
 // RN_WARPS - NF render warps through 2 NF slots; front f owns the sequence numbers k = f (mod NF).
@@ -29,13 +33,24 @@ struct PipeHeader {  // 32 bytes at the start of a slot
 
 template <bool VEC, int NF, bool DENSE>
 __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const RenderParams p, const int slot_bytes,
-                                                                    const int front_bytes) {
+                                                                    const int front_bytes,
+                                                                    const __grid_constant__ CUtensorMap tmap, const int zero_tma,
+                                                                    const int zero_tma_offset) {
     constexpr int RP_SLOTS = 2 * NF;
     constexpr int RP_RENDER_WARPS = RN_WARPS - NF;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[RP_SLOTS], s_empty[RP_SLOTS], s_stage_all[NF][2];
     __shared__ int s_ticket[RP_SLOTS];
     __shared__ double s_norm;
+    // All-zero regions (most of a sparse template) are not stored by the lanes: one elected lane hands this zero tile
+    // to the TMA engine (cp.async.bulk.tensor store, one 64 x 32 box), which keeps the LSU / register path for the
+    // regions that carry data.
+    // (the tile sits at the END of the dynamic shared memory, only when the option is on)
+    float *s_zero = reinterpret_cast<float *>(smem_raw + zero_tma_offset);
+    if (zero_tma) {
+        for (int e = threadIdx.x; e < RN_RW * RN_RH; e += RN_THREADS) s_zero[e] = 0.f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nrx = (p.W + RN_RW - 1) / RN_RW, nry = (p.H + RN_RH - 1) / RN_RH;
     const int n_regions = nrx * nry;
@@ -283,6 +298,15 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 float acc[8][8];
                 bool mma;
                 const bool any = accumulate_region<false, DENSE>(p, fs, n_live, rx0, ry0, lane, acc, hits_s, mma);
+                if (!any && zero_tma) {
+                    if (elect_one()) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmap),
+                                     "r"(smem_u32(s_zero)), "r"(rx0), "r"(ry0), "r"(t)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    continue;
+                }
                 float sc = any ? scale : 0.f;
                 if (n_pass == 2 && any && flags[reg]) {  // pin the maximum pixel to exactly 1 (see render.cu)
 #pragma unroll
@@ -295,6 +319,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             }
             mbar_arrive(&s_empty[slot]);
         }
+        if (zero_tma && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     // the last CTA to finish re-arms the ticket counters for the next launch
     __syncthreads();
@@ -324,7 +349,7 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
     if (smem > 96 * 1024) return 0;
     const bool vec = (p.W & 3) == 0;
     // DENSE: the instantiation that carries the tensor-core path (larger code; only when hit lists were set up)
-    void (*const kerns[2][3][2])(RenderParams, int, int) = {
+    void (*const kerns[2][3][2])(RenderParams, int, int, CUtensorMap, int, int) = {
         {{render_pipe_kernel<false, 1, false>, render_pipe_kernel<true, 1, false>},
          {render_pipe_kernel<false, 2, false>, render_pipe_kernel<true, 2, false>},
          {render_pipe_kernel<false, 3, false>, render_pipe_kernel<true, 3, false>}},
@@ -332,13 +357,24 @@ int launch_render_pipelined(RenderParams p, cudaStream_t st) {
          {render_pipe_kernel<false, 2, true>, render_pipe_kernel<true, 2, true>},
          {render_pipe_kernel<false, 3, true>, render_pipe_kernel<true, 3, true>}}};
     const int dense = p.hits_bytes > 0 ? 1 : 0;
-    void (*kern)(RenderParams, int, int) = kerns[dense][nf - 1][vec ? 1 : 0];
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    void (*kern)(RenderParams, int, int, CUtensorMap, int, int) = kerns[dense][nf - 1][vec ? 1 : 0];
+    // zero regions through the TMA engine: rows must be 16-byte multiples; the box is one warp region
+    alignas(64) CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int zero_tma = 0;
+    if (vec && option(OPT_RENDER_ZERO_TMA) > 0) {  // off by default: measured 4 % SLOWER on the headline (1312 vs 1262 us per 32 768 templates)
+        const int rt = make_image_tensor_map(&tmap, p.images, p.n_tmpl, p.H, p.W, RN_RW, RN_RH, false);
+        if (rt < 0) return rt;
+        zero_tma = rt == 0 ? 1 : 0;
+    }
+    const int zero_tma_offset = (int)((smem + 127) & ~(size_t)127);
+    const size_t smem_launch = zero_tma ? (size_t)zero_tma_offset + RN_RW * RN_RH * 4 : smem;
+    if (smem_launch > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RN_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RN_THREADS, smem_launch);
     if (per_sm < 1) per_sm = 1;
     const int grid = p.n_tmpl < num_sms() * per_sm ? p.n_tmpl : num_sms() * per_sm;
-    kern<<<grid, RN_THREADS, smem, st>>>(p, slot_bytes, front_bytes);
+    kern<<<grid, RN_THREADS, smem_launch, st>>>(p, slot_bytes, front_bytes, tmap, zero_tma, zero_tma_offset);
     const int rc = check_launch("ds_render (pipelined)");
     return rc == 0 ? 1 : rc;
 }

@@ -667,6 +667,25 @@ static EncodeTiledFn encode_tiled() {
     return reinterpret_cast<EncodeTiledFn>(fn);
 }
 
+// The image stack as a 3-D tensor (W, H, n_tmpl) of float32 for cp.async.bulk.tensor stores; a box is box_w x box_h pixels of
+// one template (partial boxes at the image edges are clipped by the TMA engine).  0 = ok, 1 = the driver entry point is not
+// available (callers fall back to st.global), < 0 = error.
+int make_image_tensor_map(CUtensorMap *tmap, float *images, int n_tmpl, int H, int W, int box_w, int box_h, bool swizzle128) {
+    EncodeTiledFn encode = encode_tiled();
+    if (encode == nullptr) return 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_tmpl};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1}, estr[3] = {1, 1, 1};
+    const CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, images, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("ds_render: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        return -2;
+    }
+    return 0;
+}
+
 int launch_render_prepare(const RenderParams &p, unsigned char *records, int window, cudaStream_t st);
 
 // Returns 1 if the tensor-core kernel was launched, 0 if the configuration is not eligible, < 0 on error.
@@ -677,8 +696,6 @@ bool umma_eligible(int H, int W, int cap, int radius) {
 
 int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st) {
     if (!umma_eligible(p.H, p.W, p.cap, p.radius)) return 0;
-    EncodeTiledFn encode = encode_tiled();
-    if (encode == nullptr) return 0;
     const int n8 = um_n8(p.radius);
     const int slot_bytes = umma_record_bytes(p.cap);
     // two staged tiles per epilogue warp when they fit (large capacities are tensor-pipe bound anyway)
@@ -690,18 +707,9 @@ int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st) 
     if (smem_for(2) > 226 * 1024) epi_bufs = 1;
     const size_t smem = smem_for(epi_bufs);
     if (smem > 226 * 1024) return 0;  // (+ ~1 KB of static shared memory: barriers, alignment)
-    // the image stack as a 3-D tensor (W, H, n_tmpl) of float32; a box is one 32 x 32 tile of one template
     alignas(64) CUtensorMap tmap;
-    const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_tmpl};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4};
-    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
-    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.images, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("ds_render (tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)cr);
-        return -2;
-    }
+    const int rt = make_image_tensor_map(&tmap, p.images, p.n_tmpl, p.H, p.W, 32, 32, true);
+    if (rt != 0) return rt < 0 ? rt : 0;
     const int window = option(OPT_RENDER_UMMA_WINDOW) == 0 ? 0 : 1;
     const int rc0 = launch_render_prepare(p, records, window, st);
     if (rc0 != 0) return rc0;

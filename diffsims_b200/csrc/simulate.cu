@@ -602,9 +602,10 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // Few rotations over a large table (one warp per rotation cannot fill 148 SMs): smaller CTAs spread the rotations
     // over more SMs; the table is then streamed by more CTAs, which L2 absorbs.  sim_split = 1 / 2 / 4 / 8 forces the
     // warps per CTA.
+    // Measured on the 113 082-row table (tools/bench_k12_large.py): 512 rotations 351 / 308 / 488 us with 8 / 2 / 1 warps
+    // per CTA, 2 048 rotations 428 / 993 / 1535 us.
     int wpb = SIM_WARPS;
-    while (wpb > 1 && (n_rot + wpb - 1) / wpb < 2 * num_sms()) wpb >>= 1;
-    if (n_g < 2048) wpb = SIM_WARPS;  // small tables: the launch is latency-bound either way
+    if (n_g >= 2048 && n_rot < 1024) wpb = 2;
     {
         const int o = option(OPT_SIM_SPLIT);
         if (o == 1 || o == 2 || o == 4 || o == 8) wpb = o;

@@ -112,7 +112,7 @@ structure_factor_kernel(int n_g, const double *__restrict__ hkl, const double *_
 // factorised phases (integer hkl, |h|, |k|, |l| <= H)
 // ---------------------------------------------------------------------------------------------------
 constexpr int SFT_THREADS = 256;
-constexpr int SFT_G_PER_THREAD = 3;
+constexpr int SFT_G_PER_THREAD = 1;
 constexpr int SFT_G_TILE = SFT_THREADS * SFT_G_PER_THREAD;
 
 // table[axis][atom][m + H] = (occ_j if axis == 0 else 1) * exp(2 pi i m r_j[axis]),  m = -H .. H
@@ -257,7 +257,7 @@ extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl
     if (hkl_int_max > 0 && hkl_int_max <= 127 && table_scratch != nullptr && n_atoms >= 32 && n_g >= 4096 &&
         (reinterpret_cast<uintptr_t>(table_scratch) & 15) == 0) {
         const int H = hkl_int_max, W = 2 * H + 1;
-        const size_t smem = 64 * 1024;
+        const size_t smem = 32 * 1024;
         const int smem_entries = (int)(smem / 16);  // >= 3 W for H <= 127
         double2 *table = static_cast<double2 *>(table_scratch);
         const long long n_tab = 3ll * n_atoms * W;

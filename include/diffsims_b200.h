@@ -59,6 +59,7 @@ const char *ds_last_error(void);
  *       phase-synchronous / pipelined kernels and its thresholds
  *   render_umma (DS_RENDER_UMMA) 0/1: tcgen05 K3 kernel off / forced (default: by capacity and density hint)
  *   render_umma_window (DS_RENDER_UMMA_WINDOW) 0: tcgen05 K3 kernel without per-chunk column windows
+ *   render_zero_tma (DS_RENDER_ZERO_TMA) 0: pipelined K3 kernel stores all-zero regions with st.global instead of TMA
  *   sim_lines (DS_SIM_LINES) 0/1: K2 scan-line cull off / forced
  *   sim_split (DS_SIM_SPLIT) 0/n: K2 g-table split across CTAs off / forced to n parts
  * Thread safety of the library: entry points may be called concurrently from several host threads as long

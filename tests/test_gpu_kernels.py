@@ -258,7 +258,7 @@ def test_render_graphite_golden(eng, golden_dir):
 
 
 # --------------------------------------------------------------------------- K3 schedule variants
-@pytest.mark.parametrize("variant", ["umma", "umma_nowin", "pipe", "G8", "G4", "G2", "G1"])
+@pytest.mark.parametrize("variant", ["umma", "umma_nowin", "pipe", "pipe_tma", "G8", "G4", "G2", "G1"])
 @pytest.mark.parametrize("shape,sigma", [((256, 256), 10.0), ((144, 144), 3.0), ((90, 130), 2.0)])
 def test_render_schedule_variants_agree_with_oracle(eng, opts, variant, shape, sigma):
     """The tcgen05 kernel, the warp-specialised pipelined kernel and every group size of the phase-synchronous
@@ -266,8 +266,8 @@ def test_render_schedule_variants_agree_with_oracle(eng, opts, variant, shape, s
     import torch
     if variant.startswith("umma"):
         opts(render_group=-1, render_umma=1, render_umma_window=0 if variant == "umma_nowin" else -1)
-    elif variant == "pipe":
-        opts(render_group=-1, render_pipe=1, render_umma=0)
+    elif variant.startswith("pipe"):   # all-zero regions by st.global (default) or by TMA store (option; measured slower)
+        opts(render_group=-1, render_pipe=1, render_umma=0, render_zero_tma=1 if variant == "pipe_tma" else -1)
     else:
         opts(render_group=int(variant[1:]), render_umma=0)
     phase = cases.phase("fe3c")
