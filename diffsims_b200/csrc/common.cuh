@@ -85,22 +85,35 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of
-        : "memory");                                       // polling (polls would compete with the working warps' LDS / STS)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
     return ok != 0;
 }
-// Waits are bounded: a barrier that does not complete within ~2^28 polls (each poll suspends in hardware up to the
-// hint, so this is many seconds) is a protocol bug, and the kernel traps -- the launch fails loudly with a sticky
+// Waits are bounded: a barrier that does not complete within ~2^28 polls (each try_wait suspends in hardware for a
+// while, so this is many seconds) is a protocol bug, and the kernel traps -- the launch fails loudly with a sticky
 // error instead of hanging the device.  The bound is a poll counter, not a clock read: idle roles of the
 // warp-specialised kernels sit in this loop and every instruction in it competes with the working warps.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t polls = 0;
-    while (!mbar_try(bar, phase))
-        if (++polls > (1u << 28)) __trap();
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.gt.u32 q, n, 0x10000000;\n"
+        "@q trap;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
 }
 // one elected lane of a converged warp (elect.sync): the compiler treats the predicate as warp-uniform, so uniform-
 // datapath instructions (tcgen05.mma, cp.async.bulk.tensor, ...) issue without a per-lane loop

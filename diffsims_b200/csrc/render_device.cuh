@@ -169,9 +169,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+// (spot records are rewritten between templates: volatile + memory clobber keeps the load behind the barrier / __syncwarp
+// that orders it after the writer; the tap-table loads above read data that never changes after the kernel's prologue)
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
-    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
 struct LutRef {

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
         if (lane == 0) {
             s_norm = part;
             for (int s = 0; s < RP_SLOTS; ++s) {
-                mbar_init(&s_full[s], 1);
+                mbar_init(&s_full[s], 32);  // every front lane arrives: each one releases its own writes to the slot
                 mbar_init(&s_empty[s], RP_RENDER_WARPS * 32);  // every lane arrives: its own reads of the slot are released
                 s_ticket[s] = 0;
             }
@@ -130,10 +130,8 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
             const int slot = k % RP_SLOTS, buf = j & 1;
             if (t >= p.n_tmpl) {  // out of work: hand the render warps a stop slot
                 mbar_wait(&s_empty[slot], ((uint32_t)(k / RP_SLOTS) & 1u) ^ 1u);
-                if (lane == 0) {
-                    slot_header(slot)->t = -1;
-                    mbar_arrive(&s_full[slot]);
-                }
+                if (lane == 0) slot_header(slot)->t = -1;
+                mbar_arrive(&s_full[slot]);
                 break;
             }
             const int n = min(n_next, p.cap);
@@ -266,7 +264,7 @@ __global__ void __launch_bounds__(RN_THREADS, 2) render_pipe_kernel(const Render
                 s_ticket[slot] = 0;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_full[slot]);  // release: the slot is visible to the render warps
+            mbar_arrive(&s_full[slot]);  // release (all lanes): the slot is visible to the render warps
             t = t_next;
         }
     } else {

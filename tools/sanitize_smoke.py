@@ -3,7 +3,8 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import diffsims_b200 as ds
-from diffsims_b200 import engine
+from diffsims_b200 import _cabi, engine
+from diffsims_b200.library import pack_csr
 from diffsims_b200.generators.rotation_list_generators import beam_directions_device
 from tests.golden import cases
 from tests.helpers import random_quats
@@ -14,13 +15,16 @@ for name, rr in (("si", 1.0), ("large", 1.2)):          # resident table and str
     q = random_quats(24, 0)
     for model, prec in (("lorentzian", 0.0), ("sinc", 0.0), ("lorentzian_precession", 0.0087), ("linear", 0.0087)):
         sp = engine.simulate(gt, q, gen.wavelength, 0.01, 0.01, model, precession_rad=prec, want_exc=True)
-    for variant in ("pipe", "8", "2"):
-        os.environ.pop("DS_RENDER_GROUP", None)
-        if variant != "pipe":
-            os.environ["DS_RENDER_GROUP"] = variant
+    for variant in ("umma", "pipe", "pipe_tma", "8", "2"):
+        _cabi.set_option("render_group", int(variant) if variant in ("8", "2") else -1)
+        _cabi.set_option("render_umma", 1 if variant == "umma" else 0)
+        _cabi.set_option("render_zero_tma", 1 if variant == "pipe_tma" else -1)
         for fast in (True, False):
             for shape in ((256, 256), (70, 90)):
                 engine.render(sp.count, sp.xyz, sp.intensity, shape, 6.0, rr / 64, (shape[1] // 2, shape[0] // 2), fast=fast)
+    for k in ("render_group", "render_umma", "render_zero_tma"):
+        _cabi.set_option(k, -1)
+    pack_csr(sp)
     engine.render(sp.count, sp.xyz, sp.intensity, (24, 24), 10.0, rr / 12, (12, 12))     # kernel wider than the image
     engine.polar_flatten(sp.count, sp.xyz, sp.intensity, int(sp.count.max()), np.linspace(0, 1, 20), np.linspace(-3.2, 3.2, 30))
 # dense patterns: tensor-core regions (hit lists, reflect images, lane-pair exchange), both schedules, partial regions;
@@ -32,22 +36,32 @@ for cap, shape in ((288, (256, 256)), (160, (100, 152)), (1024, (96, 200))):
     X[..., :2] = rng.uniform(-1.05, 1.05, (n, cap, 2)) * (shape[1] / 256, shape[0] / 256)
     I = rng.uniform(1, 500, (n, cap))
     cnt = torch.tensor([cap, cap // 2, 17], dtype=torch.int32, device=engine.device())
-    for pipe in ("1", "0"):
-        os.environ["DS_RENDER_PIPE"] = pipe
-        engine.render(cnt, torch.as_tensor(X, device=engine.device()), torch.as_tensor(I, device=engine.device()),
-                      shape, 7.0, 1 / 128, ((shape[1] - 1) / 2, (shape[0] - 1) / 2))
-os.environ.pop("DS_RENDER_PIPE", None)
-os.environ["DS_SIM_LINES"] = "1"
+    for umma, pipe in ((1, -1), (0, 1), (0, 0)):     # tcgen05 kernel (+ prepare pass), pipelined, phase-synchronous
+        _cabi.set_option("render_umma", umma)
+        _cabi.set_option("render_pipe", pipe)
+        for normalize in (True, False):
+            engine.render(cnt, torch.as_tensor(X, device=engine.device()), torch.as_tensor(I, device=engine.device()),
+                          shape, 7.0, 1 / 128, ((shape[1] - 1) / 2, (shape[0] - 1) / 2), normalize=normalize)
+_cabi.set_option("render_umma", -1)
+_cabi.set_option("render_pipe", -1)
+_cabi.set_option("sim_lines", 1)
 gt = gen._g_table(cases.phase("si"), 2.0, True, cases.DW)
 engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian")
 engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian_precession", precession_rad=0.0087)
 # extinct rows marked in the packed table (compact=False), culled by the plain and by the scan-line loop
 plan = gen._g_plan(cases.phase("si"), 2.0, True, {})
-for lines in ("0", "1"):
-    os.environ["DS_SIM_LINES"] = lines
+for lines in (0, 1):
+    _cabi.set_option("sim_lines", lines)
     engine.simulate(plan.run(0.5e-20, compact=False), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 engine.simulate(plan.run(0.5e-20), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
-os.environ.pop("DS_SIM_LINES", None)
+_cabi.set_option("sim_lines", -1)
+# few rotations over a large table (2 warps per CTA), the factorised structure factors (>= 4096 rows, >= 32 atoms),
+# the SO(3) grids
+plan = gen._g_plan(cases.phase("large"), 1.6, True, cases.DW)
+engine.simulate(plan.run(0.0), random_quats(40, 3), gen.wavelength, 0.01, 0.01, "lorentzian")
+from diffsims_b200.generators.rotation_list_generators import fundamental_zone_device, local_grid_device
+fundamental_zone_device(12, point_group="m-3m")
+local_grid_device(10, center=(10, 20, 30), grid_width=30)
 from diffsims_b200.pattern.detector_functions import get_pattern_from_pixel_coordinates_and_intensities
 get_pattern_from_pixel_coordinates_and_intensities(rng.uniform(-8, 98, (40, 2)), rng.uniform(20, 900, 40), (70, 90), 2.5)
 beam_directions_device("cubic", 6.0, mesh="icosahedral")
