@@ -93,25 +93,31 @@ def random_quats(n, seed):
 _CPU = {}
 
 
-def _cpu_init():
+def _cpu_init(wname="c2"):
+    """One (phase, g set, wavelength) entry per phase of the workload; c5 cycles through its three phases."""
     from oracle import kinematical as K
-    phase = si_phase()
+    w = WORKLOADS[wname]
+    _CPU.clear()
     _CPU["K"] = K
-    _CPU["phase"] = phase
-    _CPU["gs"] = K.GSet(phase.structure, WORKLOAD["rr"], True)
-    _CPU["wl"] = K.get_electron_wavelength(WORKLOAD["kv"])
+    _CPU["w"] = w
+    _CPU["wl"] = K.get_electron_wavelength(w["kv"])
+    _CPU["phases"] = []
+    for name in w["phases"]:
+        phase = bench_phase(name)
+        _CPU["phases"].append((phase, K.GSet(phase.structure, w["rr"], True)))
 
 
 def _cpu_templates(quats):
     """Spot list + rendered template for each quaternion with the float64 oracle; returns a checksum."""
     if not _CPU:
         _cpu_init()
-    K = _CPU["K"]
+    K, w = _CPU["K"], _CPU["w"]
     acc = 0.0
-    for q in quats:
+    for i, q in enumerate(quats):
+        phase, gs = _CPU["phases"][i % len(_CPU["phases"])]
         G = K.quat_to_matrix(q)  # passive matrix: rotated = g @ G
-        r = K.simulate_rotation(_CPU["phase"].structure, _CPU["gs"], G, _CPU["wl"], WORKLOAD["s_max"])
-        img = K.diffraction_pattern(r["xyz"], r["intensity"], WORKLOAD["shape"], sigma=WORKLOAD["sigma"],
+        r = K.simulate_rotation(phase.structure, gs, G, _CPU["wl"], w["s_max"])
+        img = K.diffraction_pattern(r["xyz"], r["intensity"], WORKLOAD["shape"], sigma=w["sigma"],
                                     calibration=WORKLOAD["calibration"])
         acc += float(img[128, 128])
     return acc
@@ -137,10 +143,11 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_worker = 24
+    wname = args.workload
+    per_worker = {"c4": 2, "c5": 12, "c2_dense": 12}.get(wname, 24)  # a step stays a few seconds of CPU work
     sample = cores * per_worker
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(wname,)) as pool:
         def step(seed):
             q = random_quats(sample, seed)
             chunks = [q[i * per_worker:(i + 1) * per_worker] for i in range(cores)]
@@ -155,7 +162,7 @@ def run_reference_arm(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD["workload"], templates_per_step=sample,
+                config=dict(workload=WORKLOADS[wname]["text"], workload_key=wname, templates_per_step=sample,
                             note="reference cannot be imported in this image (orix/diffpy absent); this is the "
                                  "float64 numpy port pinned by the reference's fixtures"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
