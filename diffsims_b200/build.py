@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libdiffsims_b200.so"
-SOURCES = ["cabi.cu", "structure_factor.cu", "simulate.cu", "render.cu", "render_pipe.cu", "render_umma.cu", "render_prep.cu", "polar.cu", "beam_grid.cu", "so3_grid.cu"]
+SOURCES = ["cabi.cu", "structure_factor.cu", "simulate.cu", "render.cu", "render_pipe.cu", "render_umma.cu", "render_prep.cu", "render_rows.cu", "polar.cu", "beam_grid.cu", "so3_grid.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

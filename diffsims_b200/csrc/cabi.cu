@@ -35,8 +35,12 @@ static const OptDef g_defs[OPT_COUNT] = {
     {"render_umma", "DS_RENDER_UMMA"},
     {"render_umma_window", "DS_RENDER_UMMA_WINDOW"},
     {"render_zero_tma", "DS_RENDER_ZERO_TMA"},
+    {"render_umma_team", "DS_RENDER_UMMA_TEAM"},
+    {"render_rows", "DS_RENDER_ROWS"},
     {"sim_lines", "DS_SIM_LINES"},
     {"sim_split", "DS_SIM_SPLIT"},
+    {"sim_cta", "DS_SIM_CTA"},
+    {"sim_stash", "DS_SIM_STASH"},
 };
 static std::atomic<int> g_opt[OPT_COUNT];
 static std::once_flag g_opt_once;

@@ -25,8 +25,12 @@ enum Opt {
     OPT_RENDER_UMMA,
     OPT_RENDER_UMMA_WINDOW,
     OPT_RENDER_ZERO_TMA,
+    OPT_RENDER_UMMA_TEAM,
+    OPT_RENDER_ROWS,
     OPT_SIM_LINES,
     OPT_SIM_SPLIT,
+    OPT_SIM_CTA,
+    OPT_SIM_STASH,
     OPT_COUNT
 };
 int option(Opt o);

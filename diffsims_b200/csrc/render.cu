@@ -24,6 +24,7 @@ namespace ds {
 
 int launch_render_pipelined(RenderParams p, cudaStream_t st);
 int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st);
+int launch_render_rows(RenderParams p, unsigned char *records, cudaStream_t st);
 bool umma_eligible(int H, int W, int cap, int radius);
 // the dispatch rule of ds_render for the tcgen05 path (shared with ds_render_launch_count)
 static bool wants_umma(int cap, double mean_spots_hint) {
@@ -394,7 +395,8 @@ extern "C" int ds_render_launch_count(int32_t cap, int32_t H, int32_t W, int32_t
 
 extern "C" int64_t ds_render_scratch_bytes(int32_t n_tmpl, int32_t cap) {
     if (n_tmpl < 0 || cap < 0) return -1;
-    return 16 + (int64_t)n_tmpl * ds::umma_record_bytes(cap);
+    const int a = ds::umma_record_bytes(cap), b = ds::rows_record_bytes(cap);
+    return 16 + (int64_t)n_tmpl * (a > b ? a : b);
 }
 
 extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count, const double *xyz,
@@ -496,6 +498,11 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     // float32 pipelined kernel wins below ~16 reflections per template (sigma 10), the tcgen05 kernel above.
     if (fast && !wide && !g_forced) {
         if (wants_umma(cap, mean_spots_hint)) {
+            // render_rows = 1: the row-binned banded product (render_rows.cu) instead of the per-reflection one
+            if (option(OPT_RENDER_ROWS) == 1) {
+                const int rc = launch_render_rows(p, static_cast<unsigned char *>(scratch) + 16, st);
+                if (rc != 0) return rc < 0 ? rc : 0;
+            }
             const int rc = launch_render_umma(p, static_cast<unsigned char *>(scratch) + 16, st);
             if (rc != 0) return rc < 0 ? rc : 0;
         }

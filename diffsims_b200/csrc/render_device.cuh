@@ -15,6 +15,12 @@ int num_sms();
 __host__ __device__ inline int umma_windows_offset(int cap) { return 32 + cap * 8 + 2 * cap * 2; }
 __host__ __device__ inline int umma_record_bytes(int cap) { return (umma_windows_offset(cap) + 2 * ((cap + 15) / 16) * 4 + 15) & ~15; }
 
+// record of the row-binned tcgen05 render path (render_rows.cu)
+//   int32 t, n_live, uint32 chunk mask, pad[5] | uint2 spot[cap] (column | row << 16, amplitude), ordered by row |
+//   uint16 row_offset[H + 1 <= 257, padded]
+__host__ __device__ inline int rows_offsets_offset(int cap) { return 32 + cap * 8; }
+__host__ __device__ inline int rows_record_bytes(int cap) { return (rows_offsets_offset(cap) + 2 * 264 + 15) & ~15; }
+
 constexpr int RN_WARPS = 8;
 constexpr int RN_THREADS = RN_WARPS * 32;
 constexpr int RN_RW = 64;  // warp region width  (8 lanes x 8 px)

@@ -29,19 +29,20 @@
 //
 // Reference: diffsims/pattern/detector_functions.py:293-300 (assignment + scipy.ndimage.gaussian_filter),
 // diffsims/simulations/simulation2d.py:261-285, :422-441.
-#include <cuda.h>  // CUtensorMap (types only; the encoder is looked up through the runtime)
-
 #include <atomic>
 
-#include "render_device.cuh"
+#include "umma_device.cuh"
 
 namespace ds {
 
-constexpr int UM_NP = 3;                       // operand stages = producer teams (two warps each: K groups 0 / 1 of a chunk)
+constexpr int UM_NP = 3;                       // operand stages = producer teams
 constexpr int UM_EPI = 8;                      // epilogue warps: two per tensor-memory lane quarter
-constexpr int UM_WARPS = 2 + UM_EPI + 2 * UM_NP;  // 16: four warps per scheduler, 128 registers per thread
-constexpr int UM_THREADS = UM_WARPS * 32;      // 512
-// warp roles: 0 front, 1 MMA issue, 2-3 and 12-15 producers, 4-11 epilogue (lane quarter = warp % 4)
+// TEAM = producer warps per stage.  2: one warp per K group (spots 8 kh .. 8 kh + 7) writes A and B -- 16 warps, 128
+// registers per thread.  4: per K group one warp writes A and another B -- 24 warps; the kernel starts with 80 registers
+// per thread and setmaxnreg moves them: 128 for the two epilogue warpgroups, 56 for everyone else.
+__host__ __device__ constexpr int um_warps(int team) { return team == 2 ? 16 : 24; }
+// warp roles: 0 front, 1 MMA issue, 4-11 epilogue (lane quarter = warp % 4), producers 2-3 and 12.. (TEAM = 4: the last two
+// warps of the CTA only fill their warpgroup)
 constexpr int UM_EPI_WARP0 = 4;
 constexpr int UM_A_BYTES = 128 * 16 * 2;       // one of A_hi / A_lo:  16 MN groups x 2 K groups x 128 B
 constexpr int UM_B_BYTES = 256 * 16 * 2;       // one of B_hi / B_lo:  32 MN groups x 2 K groups x 128 B
@@ -58,84 +59,6 @@ struct UmHeader {  // 32 bytes at the start of a record / slot (written by rende
 
 // entries (16 bytes = 8 taps) per shifted copy of the bf16 tap table
 __host__ __device__ inline int um_n8(int radius) { return (2 * radius + 2 * UM_BPAD + 1 + 7) / 8 + 1; }
-
-// ---- tcgen05 wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // shared-memory matrix descriptor, no swizzle: start address, leading (K-group) and stride (MN-group) byte
-    // offsets in 16-byte units, descriptor version 1 (validated by tools/microbench/umma_probe.cu)
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ uint32_t umma_idesc(int n_cols) {
-    // kind::f16: float32 accumulators, bf16 x bf16, both operands MN-major, M = 128
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
-           ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-        "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(addr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// volatile loads for shared memory that other warps (or this warp, through st.shared) rewrite between reads
-__device__ __forceinline__ float4 lds128v(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds32v(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds64v(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-
-// One 16-byte operand unit (8 consecutive pixels of one spot): split into bf16 high / low parts and store.
-__device__ __forceinline__ void store_split8(uint32_t hi_addr, uint32_t lo_addr, float4 w0, float4 w1, float a) {
-    uint32_t h[4], l[4];
-    bf16_split2(a * w0.x, a * w0.y, h[0], l[0]);
-    bf16_split2(a * w0.z, a * w0.w, h[1], l[1]);
-    bf16_split2(a * w1.x, a * w1.y, h[2], l[2]);
-    bf16_split2(a * w1.z, a * w1.w, h[3], l[3]);
-    sts128(hi_addr, h[0], h[1], h[2], h[3]);
-    sts128(lo_addr, l[0], l[1], l[2], l[3]);
-}
-
 
 // One lane's share of a chunk's A operand: four 16-byte units  a_s Wy_s[y]  for the rows 128 h + 8 (gq + 4 i) .. + 7.
 // Straight-line code (the four units overlap): a unit the spot does not reach reads the all-zero head of the tap
@@ -179,42 +102,6 @@ __device__ __forceinline__ void produce_b_border(const LutRef &L, uint32_t hi_ad
     store_split8(hi_addr, lo_addr, w0, w1, 1.0f);
 }
 
-// tcgen05.ld without the wait (the registers are only valid after tmem_wait on the same array)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-        "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(addr)
-        : "memory");
-}
-// wait for all of this thread's tensor-memory loads; the array is an in/out operand so that no use of it can be
-// scheduled ahead of the wait
-__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-// TMA store of one staged tile: box (32 columns, 32 rows, 1 template) at (x, y, t); rows / columns beyond the
-// image are clipped by the tensor map
-__device__ __forceinline__ void tma_store_tile(const CUtensorMap *tmap, uint32_t smem_src, int x, int y, int t) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_src),
-                 "r"(x), "r"(y), "r"(t)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 #ifdef DS_PROF
 // per-role cycle counters of CTA 0 (profiling builds only): [role][0] = cycles in the role's loop, [1] = of which waiting
 __device__ unsigned long long g_um_prof[4][2];
@@ -249,9 +136,12 @@ __device__ unsigned long long g_um_prof2[8];  // first epilogue warp of CTA 0: c
 #define PROF_DONE(role)
 #endif
 
-__global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const RenderParams p, const __grid_constant__ CUtensorMap tmap,
-                                                                     const unsigned char *records, const int slot_bytes,
-                                                                     const int window, const int epi_bufs) {
+template <int TEAM>
+__global__ void __launch_bounds__(um_warps(TEAM) * 32, 1) render_umma_kernel(const RenderParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                              const unsigned char *records, const int slot_bytes,
+                                                                              const int window, const int epi_bufs) {
+    constexpr int UM_PROD = TEAM * UM_NP;            // producer warps
+    constexpr int UM_THREADS = um_warps(TEAM) * 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_slot_full[UM_SLOTS], s_slot_empty[UM_SLOTS], s_stage_full[UM_NP], s_stage_empty[UM_NP],
         s_half_full[2], s_half_empty[2];
@@ -287,14 +177,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
             s_norm = part;
             for (int s = 0; s < UM_SLOTS; ++s) {
                 mbar_init(&s_slot_full[s], 1);
-                mbar_init(&s_slot_empty[s], 1 + UM_EPI + 2 * UM_NP);
+                mbar_init(&s_slot_empty[s], 1 + UM_EPI + UM_PROD);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&s_half_full[s], 1);
                 mbar_init(&s_half_empty[s], UM_EPI);
             }
             for (int s = 0; s < UM_NP; ++s) {
-                mbar_init(&s_stage_full[s], 2);
+                mbar_init(&s_stage_full[s], TEAM);
                 mbar_init(&s_stage_empty[s], 1);
             }
             fence_mbar_init();
@@ -325,7 +215,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
     }
     __syncthreads();
     const uint32_t tm = s_tmem;
-
+    // Role dispatch.  With TEAM = 4 the two epilogue warpgroups (warps 4..11) raise their register allowance and every
+    // other warpgroup lowers it; each setmaxnreg sits at the head of the branch it governs (one instruction per
+    // warpgroup, and ptxas allocates each branch against its own limit).
+    const bool epi_role = warp >= UM_EPI_WARP0 && warp < UM_EPI_WARP0 + UM_EPI;
+    if (!epi_role) {
+    if (TEAM == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // =============================== front warp ==============================================================
         PROF_DECL;
@@ -411,7 +306,112 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         }
         PROF_DONE(1);
         PROF_SEC_STORE(0, 2);
-    } else if (warp >= UM_EPI_WARP0 && warp < UM_EPI_WARP0 + UM_EPI) {
+    } else if ((warp < UM_EPI_WARP0 ? warp - 2 : warp - (UM_EPI_WARP0 + UM_EPI) + 2) < UM_PROD) {
+        // =============================== operand producers =======================================================
+        PROF_DECL;
+        PROF_SEC_DECL;
+        const int pi = warp < UM_EPI_WARP0 ? warp - 2 : warp - (UM_EPI_WARP0 + UM_EPI) + 2;  // 0 .. UM_PROD - 1
+        // team (= its stage), the K group (spots 8 kh .. 8 kh + 7) this warp writes, and which operand(s)
+        const int pw = pi / TEAM, kh = pi & 1;
+        const bool do_a = TEAM == 2 || ((pi % TEAM) >> 1) == 0, do_b = TEAM == 2 || ((pi % TEAM) >> 1) == 1;
+        const uint32_t st = smem_u32(stages) + (uint32_t)pw * UM_STAGE_BYTES;
+        const int k8 = lane & 7, gq = lane >> 3;
+        LutRef L;
+        L.base = smem_u32(lut);
+        L.n4 = p.n4;
+        L.last = p.n4 - 1;
+        L.bias = R + LUT_PAD;
+        const uint32_t bt_hi = smem_u32(btab), bt_lo = bt_hi + (uint32_t)(8 * n8 * 16);
+        const uint32_t a_hi = st + (uint32_t)(kh * (16 * 128) + k8 * 16), a_lo = a_hi + UM_A_BYTES;
+        const uint32_t b_hi = st + 2 * UM_A_BYTES + (uint32_t)(kh * (32 * 128) + k8 * 16), b_lo = b_hi + UM_B_BYTES;
+        int c = 0;
+        for (int k = 0;; ++k) {
+            const int slot = k % UM_SLOTS;
+            PROF_WAIT_BEGIN;
+            mbar_wait(&s_slot_full[slot], (uint32_t)(k / UM_SLOTS) & 1u);
+            PROF_WAIT_END;
+            const UmHeader *hd = slot_header(slot);
+            if (hd->t < 0) break;
+            const uint32_t spot_s = smem_u32(slot_spots(slot));
+            for (int h = 0; h < n_halves; ++h) {
+                const int n_h = hd->n_half[h];
+                const int n_chunks = max(1, (n_h + 15) >> 4);
+                const uint32_t list_s = smem_u32(slot_list(slot, h));
+                const uint32_t win_s = smem_u32(slots + (size_t)slot * slot_bytes + umma_windows_offset(p.cap));
+                const int win_stride = (p.cap + 15) >> 4;
+                for (int j = 0; j < n_chunks; ++j, ++c) {
+                    if (c % UM_NP != pw) continue;
+                    PROF_SEC_BEGIN;
+                    // this lane's spot of the chunk and the chunk's column window (render_prep.cu)
+                    const int li = 16 * j + 8 * kh + k8;
+                    const bool ok = li < n_h;
+                    int cx = 0, cy = 0;
+                    float am = 0.f;
+                    if (ok) {
+                        const uint2 r = lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li));
+                        cx = (int)(r.x & 0xffffu);
+                        cy = (int)(r.x >> 16);
+                        am = __uint_as_float(r.y);
+                    }
+                    const uint32_t win = lds32v(win_s + 4u * (uint32_t)(h * win_stride + j));
+                    const int col0 = (int)(win & 0xffffu), ncols = (int)(win >> 16);
+                    PROF_SEC(2);
+                    PROF_WAIT_BEGIN;
+                    mbar_wait(&s_stage_empty[pw], ((uint32_t)(c / UM_NP) & 1u) ^ 1u);
+                    PROF_WAIT_END;
+                    PROF_SEC_BEGIN;
+                    // ---- A
+                    const bool lo_half = 128 * h < R, hi_half = 128 * h + 127 >= H - R;
+                    if (!do_a) {
+                    } else if (lo_half && hi_half)
+                        produce_a<true, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else if (lo_half)
+                        produce_a<true, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else if (hi_half)
+                        produce_a<false, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    else
+                        produce_a<false, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
+                    PROF_SEC(3);
+                    // ---- B: Wx_s[x], columns col0 + 8 g .. + 7.  Blocks of four units next to a border take the float32
+                    // path with the mirror images; everything in between is a shifted copy of the pre-split table
+                    const int n_blk = ncols >> 5, n_units = do_b ? ncols >> 3 : 0;  // (ncols is a multiple of 16: the last block may be half)
+                    int g0 = do_b ? 0 : ncols;
+#pragma unroll 1
+                    for (; 8 * g0 < ncols && col0 + 8 * g0 < R; g0 += 4)
+                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
+#pragma unroll 2
+                    for (; 8 * g0 < ncols && col0 + 8 * g0 + 31 < W - R; g0 += 4) {
+                        const int g = g0 + gq, x_lo = col0 + 8 * g;
+                        const bool hit = ok && x_lo + 7 >= cx - R && x_lo <= cx + R;
+                        const int a = hit ? x_lo - cx + R + UM_BPAD : 0;  // (entry 0 of copy 0 is all zero)
+                        const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
+                        const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
+                        if (g < n_units) {
+                            sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
+                            sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
+                        }
+                    }
+#pragma unroll 1
+                    for (; 8 * g0 < ncols; g0 += 4)
+                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
+                    (void)n_blk;
+                    PROF_SEC(4);
+                    proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_stage_full[pw]);
+                    PROF_SEC(5);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
+        }
+        if (pi == 0) {
+            PROF_DONE(3);
+            PROF_SEC_STORE(2, 4);
+        }
+    }
+    } else {
+        if (TEAM == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         // =============================== epilogue ================================================================
         PROF_DECL;
         const int ew = warp - UM_EPI_WARP0;  // 0..7
@@ -542,106 +542,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) render_umma_kernel(const Render
         }
         if (elect_one()) tma_store_wait_read<0>();
         if (ew == 0) { PROF_DONE(2); }
-    } else {
-        // =============================== operand producers =======================================================
-        PROF_DECL;
-        PROF_SEC_DECL;
-        const int pi = warp < UM_EPI_WARP0 ? warp - 2 : warp - (UM_EPI_WARP0 + UM_EPI) + 2;  // 0..7
-        const int pw = pi >> 1, kh = pi & 1;  // team (= its stage), and the K group (spots 8 kh .. 8 kh + 7) this warp writes
-        const uint32_t st = smem_u32(stages) + (uint32_t)pw * UM_STAGE_BYTES;
-        const int k8 = lane & 7, gq = lane >> 3;
-        LutRef L;
-        L.base = smem_u32(lut);
-        L.n4 = p.n4;
-        L.last = p.n4 - 1;
-        L.bias = R + LUT_PAD;
-        const uint32_t bt_hi = smem_u32(btab), bt_lo = bt_hi + (uint32_t)(8 * n8 * 16);
-        const uint32_t a_hi = st + (uint32_t)(kh * (16 * 128) + k8 * 16), a_lo = a_hi + UM_A_BYTES;
-        const uint32_t b_hi = st + 2 * UM_A_BYTES + (uint32_t)(kh * (32 * 128) + k8 * 16), b_lo = b_hi + UM_B_BYTES;
-        int c = 0;
-        for (int k = 0;; ++k) {
-            const int slot = k % UM_SLOTS;
-            PROF_WAIT_BEGIN;
-            mbar_wait(&s_slot_full[slot], (uint32_t)(k / UM_SLOTS) & 1u);
-            PROF_WAIT_END;
-            const UmHeader *hd = slot_header(slot);
-            if (hd->t < 0) break;
-            const uint32_t spot_s = smem_u32(slot_spots(slot));
-            for (int h = 0; h < n_halves; ++h) {
-                const int n_h = hd->n_half[h];
-                const int n_chunks = max(1, (n_h + 15) >> 4);
-                const uint32_t list_s = smem_u32(slot_list(slot, h));
-                const uint32_t win_s = smem_u32(slots + (size_t)slot * slot_bytes + umma_windows_offset(p.cap));
-                const int win_stride = (p.cap + 15) >> 4;
-                for (int j = 0; j < n_chunks; ++j, ++c) {
-                    if (c % UM_NP != pw) continue;
-                    PROF_SEC_BEGIN;
-                    // this lane's spot of the chunk and the chunk's column window (render_prep.cu)
-                    const int li = 16 * j + 8 * kh + k8;
-                    const bool ok = li < n_h;
-                    int cx = 0, cy = 0;
-                    float am = 0.f;
-                    if (ok) {
-                        const uint2 r = lds64v(spot_s + 8u * lds16(list_s + 2u * (uint32_t)li));
-                        cx = (int)(r.x & 0xffffu);
-                        cy = (int)(r.x >> 16);
-                        am = __uint_as_float(r.y);
-                    }
-                    const uint32_t win = lds32v(win_s + 4u * (uint32_t)(h * win_stride + j));
-                    const int col0 = (int)(win & 0xffffu), ncols = (int)(win >> 16);
-                    PROF_SEC(2);
-                    PROF_WAIT_BEGIN;
-                    mbar_wait(&s_stage_empty[pw], ((uint32_t)(c / UM_NP) & 1u) ^ 1u);
-                    PROF_WAIT_END;
-                    PROF_SEC_BEGIN;
-                    // ---- A
-                    const bool lo_half = 128 * h < R, hi_half = 128 * h + 127 >= H - R;
-                    if (lo_half && hi_half)
-                        produce_a<true, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
-                    else if (lo_half)
-                        produce_a<true, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
-                    else if (hi_half)
-                        produce_a<false, true>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
-                    else
-                        produce_a<false, false>(L, a_hi, a_lo, gq, 128 * h, ok, cy, am, R, H);
-                    PROF_SEC(3);
-                    // ---- B: Wx_s[x], columns col0 + 8 g .. + 7.  Blocks of four units next to a border take the float32
-                    // path with the mirror images; everything in between is a shifted copy of the pre-split table
-                    const int n_blk = ncols >> 5, n_units = ncols >> 3;  // (ncols is a multiple of 16: the last block may be half)
-                    int g0 = 0;
-#pragma unroll 1
-                    for (; 8 * g0 < ncols && col0 + 8 * g0 < R; g0 += 4)
-                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
-#pragma unroll 2
-                    for (; 8 * g0 < ncols && col0 + 8 * g0 + 31 < W - R; g0 += 4) {
-                        const int g = g0 + gq, x_lo = col0 + 8 * g;
-                        const bool hit = ok && x_lo + 7 >= cx - R && x_lo <= cx + R;
-                        const int a = hit ? x_lo - cx + R + UM_BPAD : 0;  // (entry 0 of copy 0 is all zero)
-                        const uint32_t off = (uint32_t)(((a & 7) * n8 + (a >> 3)) << 4);
-                        const uint4 vh = lds128u(bt_hi + off), vl = lds128u(bt_lo + off);
-                        if (g < n_units) {
-                            sts128(b_hi + 128u * g, vh.x, vh.y, vh.z, vh.w);
-                            sts128(b_lo + 128u * g, vl.x, vl.y, vl.z, vl.w);
-                        }
-                    }
-#pragma unroll 1
-                    for (; 8 * g0 < ncols; g0 += 4)
-                        if (g0 + gq < n_units) produce_b_border(L, b_hi + 128u * (g0 + gq), b_lo + 128u * (g0 + gq), col0 + 8 * (g0 + gq), ok, cx, R, W);
-                    (void)n_blk;
-                    PROF_SEC(4);
-                    proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_stage_full[pw]);
-                    PROF_SEC(5);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
-        }
-        if (pi == 0) {
-            PROF_DONE(3);
-            PROF_SEC_STORE(2, 4);
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -713,10 +613,18 @@ int launch_render_umma(RenderParams p, unsigned char *records, cudaStream_t st) 
     const int window = option(OPT_RENDER_UMMA_WINDOW) == 0 ? 0 : 1;
     const int rc0 = launch_render_prepare(p, records, window, st);
     if (rc0 != 0) return rc0;
-    cudaFuncSetAttribute(render_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const int sms = num_sms();
     const int grid = p.n_tmpl < sms ? p.n_tmpl : sms;
-    render_umma_kernel<<<grid, UM_THREADS, smem, st>>>(p, tmap, records, slot_bytes, window, epi_bufs);
+    // producer warps per operand stage: 2; render_umma_team = 4 puts A and B of a K group on separate warps (24 warps,
+    // setmaxnreg) -- measured 3 - 6 % slower on every configuration (the shared-memory pipe, not producer latency, is the
+    // limit), kept for the A/B measurement
+    if (option(OPT_RENDER_UMMA_TEAM) != 4) {
+        cudaFuncSetAttribute(render_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        render_umma_kernel<2><<<grid, um_warps(2) * 32, smem, st>>>(p, tmap, records, slot_bytes, window, epi_bufs);
+    } else {
+        cudaFuncSetAttribute(render_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        render_umma_kernel<4><<<grid, um_warps(4) * 32, smem, st>>>(p, tmap, records, slot_bytes, window, epi_bufs);
+    }
     const int rc = check_launch("ds_render (tcgen05)");
     return rc == 0 ? 1 : rc;
 }

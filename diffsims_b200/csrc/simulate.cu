@@ -100,16 +100,36 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 }
 
 // float32 coarse test of one g (z' = R[2,:].g, r^2 = |g|^2 - z'^2): cancellation-free and sqrt-free,
-//   |s| < t  <=>  f(z'+t) < 0 < f(z'-t),  f(u) = r^2 + u (u - 2 r_s);
-// with precession the two-surface test of simulation_generator.py:365-375 in the same algebra around the
-// tilted sphere centre (P_t, P_z).
-__device__ __forceinline__ bool coarse_test(float z, float g2, float thr, float two_rs, bool prec_on, float P_z,
-                                            float P_t) {
+//   |s| < t  <=>  f(z'+t) < 0 < f(z'-t),  f(u) = r^2 + u (u - 2 r_s).
+// Both f values are linear in z': f(z' -+ t) = q +- d with q = |g|^2 + t^2 - 2 r_s z' and d = 2 t (r_s - z') > 0, so the
+// test is |q| < d: two FFMA, one FADD and one compare after the three FFMA of z'.  Rows with |g|^2 = +inf (extinct rows,
+// tail padding) give q = +inf and fail.  With precession the two-surface test of simulation_generator.py:365-375 in the
+// same algebra around the tilted sphere centre (P_t, P_z).
+struct CoarseConst {
+    float two_rs, thr, t2, two_t, two_t_rs, P_z, P_t;
+    bool prec_on;
+};
+__device__ __forceinline__ bool coarse_test(float z, float g2, const CoarseConst &c) {
+    if (!c.prec_on) {
+        const float q = fmaf(-c.two_rs, z, g2 + c.t2), d = fmaf(-c.two_t, z, c.two_t_rs);
+        return fabsf(q) < d;
+    }
     const float r2 = fmaf(-z, z, g2);
-    const float u = z + thr, v = z - thr;
-    if (!prec_on) return (fmaf(u, u - two_rs, r2) < 0.0f) && (fmaf(v, v - two_rs, r2) > 0.0f);
-    const float r = sqrtf(fmaxf(r2, 0.0f)), two_rpt = 2.0f * r * P_t;
-    return (r2 + two_rpt + v * (v - 2.0f * P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * P_z) <= 0.0f);
+    const float u = z + c.thr, v = z - c.thr;
+    const float r = sqrtf(fmaxf(r2, 0.0f)), two_rpt = 2.0f * r * c.P_t;
+    return (r2 + two_rpt + v * (v - 2.0f * c.P_z) >= 0.0f) && (r2 - two_rpt + u * (u - 2.0f * c.P_z) <= 0.0f);
+}
+__device__ __forceinline__ CoarseConst coarse_const(double rs, double s_max, float margin, double prec, bool general) {
+    CoarseConst c;
+    c.two_rs = 2.0f * (float)rs;
+    c.thr = (float)s_max + margin;
+    c.t2 = c.thr * c.thr;
+    c.two_t = 2.0f * c.thr;
+    c.two_t_rs = c.two_t * (float)rs;
+    c.prec_on = general && prec != 0.0;
+    c.P_z = general ? (float)(rs * cos(prec)) : 0.f;
+    c.P_t = general ? (float)(rs * sin(prec)) : 0.f;
+    return c;
 }
 
 // scan-line mode rebuilds g from the line tables; rows marked extinct by ds_pack_gtable (|g|^2 = +inf in the packed
@@ -125,35 +145,44 @@ struct WarpState {
     double max_I;  // running max of their intensities
 };
 
-// Refine up to 32 candidates (one per lane) in float64 and append the survivors to the output row.
-// MODEL >= 0 fixes the shape factor at compile time (no precession); MODEL < 0 is the general kernel
-// (runtime model, precession cut, closed-form or numerically averaged precession shape factor).
-template <int MODEL>
-__device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot, bool have, int gi, int lane,
-                                       const double *__restrict__ s_cos) {
+// Float64 evaluation of up to 32 candidates (one per lane): full rotation, the reference's own excitation-error
+// expression, the strict cut, shape factor and intensity.  MODEL >= 0 fixes the shape factor at compile time (no
+// precession); MODEL < 0 is the general kernel (runtime model, precession cut, closed-form or numerically averaged
+// precession shape factor -- the average is warp-cooperative, so all 32 lanes must call this).  WITH_I = false stops
+// after the cut (x, y, z, s only).
+struct Refined {
+    double x, y, z, s, I;
+    bool keep;
+};
+template <int MODEL, bool WITH_I>
+__device__ __forceinline__ Refined refine_eval(const SimParams &p, const double (&m)[9], bool have, int gi, int lane,
+                                               const double *__restrict__ s_cos) {
     constexpr bool GENERAL = MODEL < 0;
     const int model = GENERAL ? p.model : MODEL;
-    bool keep = false;
-    double x = 0, y = 0, z = 0, s = 0, I = 0, r_spot = 0;
+    Refined r;
+    r.keep = false;
+    r.x = r.y = r.z = r.s = r.I = 0.0;
+    double r_spot = 0;
     if (have) {
         const double gx = __ldg(p.g_xyz + 3 * (size_t)gi), gy = __ldg(p.g_xyz + 3 * (size_t)gi + 1),
                      gz = __ldg(p.g_xyz + 3 * (size_t)gi + 2);
-        x = w.m[0] * gx + w.m[1] * gy + w.m[2] * gz;
-        y = w.m[3] * gx + w.m[4] * gy + w.m[5] * gz;
-        z = w.m[6] * gx + w.m[7] * gy + w.m[8] * gz;
+        r.x = m[0] * gx + m[1] * gy + m[2] * gz;
+        r.y = m[3] * gx + m[4] * gy + m[5] * gz;
+        r.z = m[6] * gx + m[7] * gy + m[8] * gz;
         // simulation_generator.py:355-360, evaluated as the reference writes it
-        r_spot = sqrt(x * x + y * y);
+        r_spot = sqrt(r.x * r.x + r.y * r.y);
         const double z_sphere = -sqrt(p.rs * p.rs - r_spot * r_spot) + p.rs;
-        s = z_sphere - z;
+        r.s = z_sphere - r.z;
         if (!GENERAL || p.prec == 0.0) {
-            keep = fabs(s) < p.s_max;  // :364 strict
-        } else {                       // :365-375
+            r.keep = fabs(r.s) < p.s_max;  // :364 strict
+        } else {                           // :365-375
             const double P_z = p.rs * cos(p.prec), P_t = p.rs * sin(p.prec);
             const double up = P_z - sqrt(p.rs * p.rs - (r_spot + P_t) * (r_spot + P_t));
             const double dn = P_z - sqrt(p.rs * p.rs - (r_spot - P_t) * (r_spot - P_t));
-            keep = (z - p.s_max <= up) && (z + p.s_max >= dn);
+            r.keep = (r.z - p.s_max <= up) && (r.z + p.s_max >= dn);
         }
     }
+    if (!WITH_I) return r;
     double sf = 1.0;
     if (GENERAL && p.n_quad > 0) {
         // _shape_factor_precession (shape_factor_models.py:222-269): (1 / 2 pi) int_0^2pi f(s + r phi cos t) dt.
@@ -161,8 +190,8 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
         // u = cos t) converges geometrically for the smooth models and as 1/n^2 for the kinked ones; the
         // whole warp integrates one candidate at a time over a cosine table in shared memory.
         for (int c = 0; c < 32; ++c) {
-            if (!__shfl_sync(0xffffffffu, (int)keep, c)) continue;
-            const double sc = __shfl_sync(0xffffffffu, s, c);
+            if (!__shfl_sync(0xffffffffu, (int)r.keep, c)) continue;
+            const double sc = __shfl_sync(0xffffffffu, r.s, c);
             const double amp = __shfl_sync(0xffffffffu, r_spot, c) * p.prec;
             double acc = 0.0;
             for (int j = lane; j < p.n_quad; j += 32)
@@ -171,34 +200,100 @@ __device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == c) sf = acc / (double)p.n_quad;
         }
-    } else if (keep) {
-        sf = shape_factor(model, s, p.width, p.minima, r_spot, GENERAL ? p.prec : 0.0);
+    } else if (r.keep) {
+        sf = shape_factor(model, r.s, p.width, p.minima, r_spot, GENERAL ? p.prec : 0.0);
     }
-    if (keep) I = sf * __ldg(p.g_I0 + gi);
-    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (r.keep) r.I = sf * __ldg(p.g_I0 + gi);
+    return r;
+}
+
+// Refine up to 32 candidates and append the survivors to the output row.
+template <int MODEL>
+__device__ __forceinline__ void refine(const SimParams &p, WarpState &w, int rot, bool have, int gi, int lane,
+                                       const double *__restrict__ s_cos) {
+    const Refined r = refine_eval<MODEL, true>(p, w.m, have, gi, lane, s_cos);
+    const unsigned mask = __ballot_sync(0xffffffffu, r.keep);
     const int slot = w.n_out + __popc(mask & ((1u << lane) - 1u));
-    if (keep && slot < p.cap) {
+    if (r.keep && slot < p.cap) {
         const size_t o = (size_t)rot * p.cap + slot;
-        p.xyz[3 * o + 0] = x;
-        p.xyz[3 * o + 1] = y;
-        p.xyz[3 * o + 2] = z;
-        p.intensity[o] = I;
+        p.xyz[3 * o + 0] = r.x;
+        p.xyz[3 * o + 1] = r.y;
+        p.xyz[3 * o + 2] = r.z;
+        p.intensity[o] = r.I;
         p.g_index[o] = gi;
-        if (p.exc) p.exc[o] = s;
+        if (p.exc) p.exc[o] = r.s;
     }
     w.n_out += __popc(mask);
-    w.max_I = fmax(w.max_I, warp_max(keep ? I : -INFINITY));
+    w.max_I = fmax(w.max_I, warp_max(r.keep ? r.I : -INFINITY));
+}
+
+// Active rotation matrix of a unit quaternion (a, b, c, d), row-major float64.
+__device__ __forceinline__ void quat_matrix(const double *__restrict__ q, double (&m)[9]) {
+    const double a = q[0], b = q[1], c = q[2], d = q[3];
+    m[0] = a * a + b * b - c * c - d * d;
+    m[1] = 2 * (b * c - a * d);
+    m[2] = 2 * (b * d + a * c);
+    m[3] = 2 * (b * c + a * d);
+    m[4] = a * a - b * b + c * c - d * d;
+    m[5] = 2 * (c * d - a * b);
+    m[6] = 2 * (b * d - a * c);
+    m[7] = 2 * (c * d + a * b);
+    m[8] = a * a - b * b - c * c + d * d;
+}
+
+// The minimum-intensity cut of one stored row, in place and in order (simulation_generator.py:237): one warp.
+template <int MODEL>
+__device__ __forceinline__ int threshold_row(const SimParams &p, int rot, int n_out, double max_I, int lane) {
+    constexpr bool GENERAL = MODEL < 0;
+    const int n_stored = min(n_out, p.cap);
+    if ((GENERAL ? p.model : MODEL) == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0) return n_stored;  // cut disabled
+    int n_keep = 0;
+    const double cut = max_I * p.min_intensity;
+    const size_t row = (size_t)rot * p.cap;
+    for (int j0 = 0; j0 < n_stored; j0 += 32) {
+        const int j = j0 + lane;
+        bool keep = false;
+        double x = 0, y = 0, z = 0, I = 0, s = 0;
+        int gi = 0;
+        if (j < n_stored) {
+            I = p.intensity[row + j];
+            keep = I > cut;
+            if (keep) {
+                x = p.xyz[3 * (row + j)];
+                y = p.xyz[3 * (row + j) + 1];
+                z = p.xyz[3 * (row + j) + 2];
+                gi = p.g_index[row + j];
+                if (p.exc) s = p.exc[row + j];
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int dst = n_keep + __popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+        if (keep && dst != j) {
+            p.xyz[3 * (row + dst)] = x;
+            p.xyz[3 * (row + dst) + 1] = y;
+            p.xyz[3 * (row + dst) + 2] = z;
+            p.intensity[row + dst] = I;
+            p.g_index[row + dst] = gi;
+            if (p.exc) p.exc[row + dst] = s;
+        }
+        n_keep += __popc(mask);
+        __syncwarp();
+    }
+    return n_keep;
 }
 
 template <int MODEL, bool LINES>
 __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kernel(const SimParams p, const int n_tiles,
-                                                                  const int tile_g) {
+                                                                  const int tile_g, const int tile_alloc) {
     constexpr bool GENERAL = MODEL < 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // `tile_alloc` rows per buffer: tile_g rounded up to a multiple of 128 (the brute-force scan reads 128 rows per step
+    // without bounds checks; the rows past a tile's end hold |g|^2 = +inf and fail the test).  In scan-line mode the host
+    // passes tile_g = tile_alloc = bytes of the line tables / 16, n_tiles = 1.
     float4 *s_tile[2] = {reinterpret_cast<float4 *>(smem_raw),
-                         reinterpret_cast<float4 *>(smem_raw) + (n_tiles > 1 ? tile_g : 0)};
-    // (in scan-line mode the host passes tile_g = bytes of the line tables / 16, n_tiles = 1)
-    double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1));
+                         reinterpret_cast<float4 *>(smem_raw) + (n_tiles > 1 ? tile_alloc : 0)};
+    double *s_cos = reinterpret_cast<double *>(smem_raw + (size_t)tile_alloc * 16 * (n_tiles > 1 ? 2 : 1));
     if (GENERAL)
         for (int j = threadIdx.x; j < p.n_quad; j += blockDim.x) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -235,13 +330,19 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
         s_lstart = dst1;
     } else if (n_tiles == 1) {  // resident table: one bulk copy for the CTA's lifetime
         issue(0, 0);
+        for (int i = p.n_g + (int)threadIdx.x; i < tile_alloc; i += blockDim.x) s_tile[0][i] = make_float4(0.f, 0.f, 0.f, INFINITY);
         mbar_wait(&s_bar[0], 0);
+        __syncthreads();
     }
+    // streaming: the last tile is short; its buffer's rows up to the next multiple of 128 are re-padded every time it is
+    // issued (the full tile that used the buffer before overwrote them)
+    const int n_last = p.n_g - (n_tiles - 1) * tile_g;
+    auto pad_last = [&](int buf) {
+        for (int i = n_last + (int)threadIdx.x; i < ((n_last + 127) & ~127); i += blockDim.x)
+            s_tile[buf][i] = make_float4(0.f, 0.f, 0.f, INFINITY);
+    };
 
-    const float two_rs = 2.0f * (float)p.rs;
-    const float thr = (float)p.s_max + p.coarse_margin;
-    const bool prec_on = GENERAL && p.prec != 0.0;
-    const float P_z = GENERAL ? (float)(p.rs * cos(p.prec)) : 0.f, P_t = GENERAL ? (float)(p.rs * sin(p.prec)) : 0.f;
+    const CoarseConst cc = coarse_const(p.rs, p.s_max, p.coarse_margin, p.prec, GENERAL);
     const uint32_t tile_base_s = smem_u32(smem_raw);
     int local_max_count = 0;
 
@@ -256,17 +357,7 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
         w.max_I = -INFINITY;
         float mz0 = 0, mz1 = 0, mz2 = 0;
         if (active) {
-            const double a = p.quat[4 * (size_t)rot], b = p.quat[4 * (size_t)rot + 1],
-                         c = p.quat[4 * (size_t)rot + 2], d = p.quat[4 * (size_t)rot + 3];
-            w.m[0] = a * a + b * b - c * c - d * d;
-            w.m[1] = 2 * (b * c - a * d);
-            w.m[2] = 2 * (b * d + a * c);
-            w.m[3] = 2 * (b * c + a * d);
-            w.m[4] = a * a - b * b + c * c - d * d;
-            w.m[5] = 2 * (c * d - a * b);
-            w.m[6] = 2 * (b * d - a * c);
-            w.m[7] = 2 * (c * d + a * b);
-            w.m[8] = a * a - b * b - c * c + d * d;
+            quat_matrix(p.quat + 4 * (size_t)rot, w.m);
             mz0 = (float)w.m[6];
             mz1 = (float)w.m[7];
             mz2 = (float)w.m[8];
@@ -339,7 +430,7 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                             const float gx = fmaf(fi, p.step[0], g0.x), gy = fmaf(fi, p.step[1], g0.y),
                                         gz = fmaf(fi, p.step[2], g0.z);
                             const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
-                            if (coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t) &&
+                            if (coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), cc) &&
                                 live_row(p, start + ilo + r))
                                 bits |= 1u << r;
                         }
@@ -390,7 +481,7 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                                 const float gx = fmaf(fi, p.step[0], hx), gy = fmaf(fi, p.step[1], hy),
                                             gz = fmaf(fi, p.step[2], hz);
                                 const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
-                                cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), thr, two_rs, prec_on, P_z, P_t) &&
+                                cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), cc) &&
                                        live_row(p, first + r);
                             }
                             append(cand, first + r);
@@ -403,12 +494,15 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
             for (int t = 0; t < n_tiles; ++t) {
                 const int buf = (n_tiles > 1) ? (t & 1) : 0;
                 if (n_tiles > 1) {
-                    if (t + 1 < n_tiles) issue(t + 1, (t + 1) & 1);
+                    if (t + 1 < n_tiles) {
+                        issue(t + 1, (t + 1) & 1);
+                        if (t + 2 == n_tiles) pad_last((t + 1) & 1);  // (read after the __syncthreads that ends this tile)
+                    }
                     mbar_wait(&s_bar[buf], phase[buf]);
                     phase[buf] ^= 1;
                 }
                 const int n = min(tile_g, p.n_g - t * tile_g);
-                const uint32_t tile_s = tile_base_s + (buf ? (uint32_t)tile_g * 16u : 0u);
+                const uint32_t tile_s = tile_base_s + (buf ? (uint32_t)tile_alloc * 16u : 0u);
                 if (active) {
                     for (int i0 = 0; i0 < n; i0 += 128) {
                         // four independent g per lane: loads and tests overlap, ballots are consumed in table order
@@ -416,13 +510,13 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
                         float4 gk[4];
     #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            gk[k] = lds_f4(tile_s + 16u * (uint32_t)min(i0 + 32 * k + lane, n - 1));
+                            gk[k] = lds_f4(tile_s + 16u * (uint32_t)(i0 + 32 * k + lane));
                         bool any = false;
     #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float4 g = gk[k];
                             const float z = fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z));
-                            cands[k] = coarse_test(z, g.w, thr, two_rs, prec_on, P_z, P_t) && (i0 + 32 * k + lane < n);
+                            cands[k] = coarse_test(z, g.w, cc);
                             any |= cands[k];
                         }
                         if (!__any_sync(0xffffffffu, any)) continue;
@@ -437,47 +531,221 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
             if (n_list > 0) refine<MODEL>(p, w, rot, lane < n_list, lane < n_list ? list[lane] : 0, lane, s_cos);
             __syncwarp();
             local_max_count = max(local_max_count, w.n_out);
-            // ---- threshold: keep I > max(I) * min_intensity (simulation_generator.py:237), in place
-            const int n_stored = min(w.n_out, p.cap);
-            int n_keep = 0;
-            if ((GENERAL ? p.model : MODEL) == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0) {  // threshold disabled
-                n_keep = n_stored;
-            } else {
-                const double cut = w.max_I * p.min_intensity;
-                const size_t row = (size_t)rot * p.cap;
-                for (int j0 = 0; j0 < n_stored; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool keep = false;
-                    double x = 0, y = 0, z = 0, I = 0, s = 0;
-                    int gi = 0;
-                    if (j < n_stored) {
-                        I = p.intensity[row + j];
-                        keep = I > cut;
-                        if (keep) {
-                            x = p.xyz[3 * (row + j)];
-                            y = p.xyz[3 * (row + j) + 1];
-                            z = p.xyz[3 * (row + j) + 2];
-                            gi = p.g_index[row + j];
-                            if (p.exc) s = p.exc[row + j];
-                        }
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, keep);
-                    const int dst = n_keep + __popc(mask & ((1u << lane) - 1u));
-                    __syncwarp();
-                    if (keep && dst != j) {
-                        p.xyz[3 * (row + dst)] = x;
-                        p.xyz[3 * (row + dst) + 1] = y;
-                        p.xyz[3 * (row + dst) + 2] = z;
-                        p.intensity[row + dst] = I;
-                        p.g_index[row + dst] = gi;
-                        if (p.exc) p.exc[row + dst] = s;
-                    }
-                    n_keep += __popc(mask);
-                    __syncwarp();
-                }
-            }
+            const int n_keep = threshold_row<MODEL>(p, rot, w.n_out, w.max_I, lane);
             if (lane == 0) p.count[rot] = n_keep;
         }
+    }
+    local_max_count = warp_max(local_max_count);
+    if (lane == 0 && local_max_count > 0) atomicMax(p.max_count, local_max_count);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Few rotations over a large table: one CTA per rotation, the table split across the CTA's warps.
+//
+// With one warp per rotation a launch of a few hundred rotations over a 10^5-row table is bound by one warp's latency over
+// the whole table.  Here the eight warps of a CTA scan eight contiguous slices of the table (straight from L2 / L1: the
+// CTAs of an SM run in step and share the lines), so the rotation's reflections come out in table order as slice 0,
+// slice 1, ...:
+//   1. scan: float32 coarse test, candidate row indices into the stash (shared memory).  The stash is one pool of
+//      64-entry chunks that the warps draw from as they fill up -- the slab of a zone-axis-like orientation puts most
+//      candidates into one or two slices;
+//   2. evaluate the candidates in float64 (refine_eval), intensities into the stash (NaN = failed the cut);
+//      CTA-wide: number of reflections before the intensity cut (max_count) and their maximum -> the cut;
+//   3. count the survivors per warp, CTA prefix sum -> each warp's offset in the output row;
+//   4. re-evaluate the survivors' geometry (bit-identical: same code) and store them at their final positions.
+// A rotation with more candidates than the pool holds goes to warp 0, which runs the one-warp algorithm of
+// simulate_kernel straight from global memory.  Results are identical to simulate_kernel's whenever max_count <= cap (the
+// only case callers accept).
+// ---------------------------------------------------------------------------------------------------
+constexpr int SIM_CHUNK = 64;        // stash entries per chunk
+constexpr int SIM_MAX_CHUNKS = 255;  // chunk ids are bytes
+
+template <int MODEL>
+__global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimParams p, const int n_chunks) {
+    constexpr bool GENERAL = MODEL < 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [n_chunks][64] intensities (double) | same shape candidate rows (int) | [warps][n_chunks] chunk ids | cosine table
+    double *s_I = reinterpret_cast<double *>(smem_raw);
+    int *s_cand = reinterpret_cast<int *>(s_I + (size_t)n_chunks * SIM_CHUNK);
+    unsigned char *s_ids = reinterpret_cast<unsigned char *>(s_cand + (size_t)n_chunks * SIM_CHUNK);
+    double *s_cos = reinterpret_cast<double *>(s_ids + (((size_t)SIM_WARPS * n_chunks + 15) & ~(size_t)15));
+    if (GENERAL)
+        for (int j = threadIdx.x; j < p.n_quad; j += blockDim.x) s_cos[j] = cospi(((double)j + 0.5) / (double)p.n_quad);
+    __shared__ int s_ncand[SIM_WARPS], s_nout[SIM_WARPS], s_nkeep[SIM_WARPS];
+    __shared__ double s_wmax[SIM_WARPS];
+    __shared__ int s_next;      // next free chunk of the pool
+    __shared__ int s_list[64];  // fall-back: warp 0's candidate list
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CoarseConst cc = coarse_const(p.rs, p.s_max, p.coarse_margin, p.prec, GENERAL);
+    // this warp's slice of the table: a multiple of 128 rows
+    const int per_warp = ((p.n_g + SIM_WARPS * 128 - 1) / (SIM_WARPS * 128)) * 128;
+    const int row_lo = min(p.n_g, warp * per_warp), row_hi = min(p.n_g, row_lo + per_warp);
+    const bool cut_off = (GENERAL ? p.model : MODEL) == DS_SHAPE_NONE_RETURN_S || p.min_intensity < 0.0;
+    unsigned char *my_ids = s_ids + (size_t)warp * n_chunks;
+    // stash position of this warp's j-th candidate
+    auto at = [&](int j) { return (int)my_ids[j / SIM_CHUNK] * SIM_CHUNK + (j % SIM_CHUNK); };
+    int local_max_count = 0;
+
+    for (int rot = blockIdx.x; rot < p.n_rot; rot += gridDim.x) {
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();  // (also: the previous rotation's stash has been consumed)
+        double m[9];
+        quat_matrix(p.quat + 4 * (size_t)rot, m);
+        const float mz0 = (float)m[6], mz1 = (float)m[7], mz2 = (float)m[8];
+        // ---- 1. scan this warp's slice
+        int n_c = 0, n_have = 0;  // candidates so far (counted on even when the pool is exhausted); chunks held
+        bool full = false;
+        // (the rows of the next step are requested before this step's are tested: a slice streams from L2 at a few hundred
+        // nanoseconds per round trip, and a CTA per SM has only eight warps to hide it)
+        auto fetch = [&](int i0, float4 (&g)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + 32 * k + lane;
+                g[k] = i < row_hi ? __ldg(p.g_f32 + i) : make_float4(0.f, 0.f, 0.f, INFINITY);
+            }
+        };
+        float4 nxt[4];
+        fetch(row_lo, nxt);
+        for (int i0 = row_lo; i0 < row_hi; i0 += 128) {
+            float4 gk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gk[k] = nxt[k];
+            fetch(i0 + 128, nxt);
+            bool cands[4], any = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cands[k] = coarse_test(fmaf(mz0, gk[k].x, fmaf(mz1, gk[k].y, mz2 * gk[k].z)), gk[k].w, cc);
+                any |= cands[k];
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned mask = __ballot_sync(0xffffffffu, cands[k]);
+                if (mask == 0u) continue;
+                const int n_new = __popc(mask);
+                if (!full && n_c + n_new > n_have * SIM_CHUNK) {  // (at most one more chunk: 32 <= SIM_CHUNK)
+                    int id = 0;
+                    if (lane == 0) id = atomicAdd(&s_next, 1);
+                    id = __shfl_sync(0xffffffffu, id, 0);
+                    if (id < n_chunks) {
+                        if (lane == 0) my_ids[n_have] = (unsigned char)id;
+                        ++n_have;
+                        __syncwarp();
+                    } else {
+                        full = true;
+                    }
+                }
+                const int j = n_c + __popc(mask & ((1u << lane) - 1u));
+                if (cands[k] && j < n_have * SIM_CHUNK) s_cand[at(j)] = i0 + 32 * k + lane;
+                n_c += n_new;
+            }
+        }
+        if (lane == 0) s_ncand[warp] = full ? -1 : n_c;
+        __syncthreads();
+        bool overflow = false;
+        for (int w = 0; w < SIM_WARPS; ++w) overflow |= s_ncand[w] < 0;
+        if (overflow) {
+            // ---- fall-back: warp 0 alone, the one-warp algorithm over the whole table
+            if (warp == 0) {
+                WarpState ws;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) ws.m[k] = m[k];
+                ws.n_out = 0;
+                ws.max_I = -INFINITY;
+                int n_list = 0;
+                for (int i0 = 0; i0 < p.n_g; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool cand = false;
+                    if (i < p.n_g) {
+                        const float4 g = __ldg(p.g_f32 + i);
+                        cand = coarse_test(fmaf(mz0, g.x, fmaf(mz1, g.y, mz2 * g.z)), g.w, cc);
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                    if (mask == 0u) continue;
+                    if (cand) s_list[n_list + __popc(mask & ((1u << lane) - 1u))] = i;
+                    n_list += __popc(mask);
+                    __syncwarp();
+                    if (n_list >= 32) {
+                        refine<MODEL>(p, ws, rot, true, s_list[lane], lane, s_cos);
+                        const int rest = n_list - 32;
+                        const int carry = (lane < rest) ? s_list[32 + lane] : 0;
+                        __syncwarp();
+                        s_list[lane] = carry;
+                        n_list = rest;
+                        __syncwarp();
+                    }
+                }
+                if (n_list > 0) refine<MODEL>(p, ws, rot, lane < n_list, lane < n_list ? s_list[lane] : 0, lane, s_cos);
+                __syncwarp();
+                local_max_count = max(local_max_count, ws.n_out);
+                const int n_keep = threshold_row<MODEL>(p, rot, ws.n_out, ws.max_I, lane);
+                if (lane == 0) p.count[rot] = n_keep;
+            }
+            continue;  // (uniform: the flags are in shared memory)
+        }
+        // ---- 2. float64 evaluation of this warp's candidates
+        int n_out = 0;
+        double max_I = -INFINITY;
+        for (int j0 = 0; j0 < n_c; j0 += 32) {
+            const int j = j0 + lane;
+            const bool have = j < n_c;
+            const int pos = have ? at(j) : 0;
+            const Refined e = refine_eval<MODEL, true>(p, m, have, have ? s_cand[pos] : 0, lane, s_cos);
+            if (have) s_I[pos] = e.keep ? e.I : __longlong_as_double(0x7ff8000000000000ll);
+            n_out += __popc(__ballot_sync(0xffffffffu, e.keep));
+            max_I = fmax(max_I, e.keep ? e.I : -INFINITY);
+        }
+        max_I = warp_max(max_I);
+        if (lane == 0) {
+            s_nout[warp] = n_out;
+            s_wmax[warp] = max_I;
+        }
+        __syncthreads();
+        int total_out = 0;
+        double row_max = -INFINITY;
+        for (int w = 0; w < SIM_WARPS; ++w) {
+            total_out += s_nout[w];
+            row_max = fmax(row_max, s_wmax[w]);
+        }
+        local_max_count = max(local_max_count, total_out);
+        // ---- 3. survivors of the intensity cut per warp (NaN compares false; cut disabled: everything that is not NaN)
+        const double cut = cut_off ? -INFINITY : row_max * p.min_intensity;
+        int n_keep = 0;
+        for (int j0 = 0; j0 < n_c; j0 += 32) {
+            const int j = j0 + lane;
+            const double I = j < n_c ? s_I[at(j)] : __longlong_as_double(0x7ff8000000000000ll);
+            n_keep += __popc(__ballot_sync(0xffffffffu, cut_off ? I == I : I > cut));
+        }
+        if (lane == 0) s_nkeep[warp] = n_keep;
+        __syncthreads();
+        int offset = 0, total_keep = 0;
+        for (int w = 0; w < SIM_WARPS; ++w) {
+            if (w < warp) offset += s_nkeep[w];
+            total_keep += s_nkeep[w];
+        }
+        // ---- 4. geometry again for the survivors, stored at their final positions
+        for (int j0 = 0; j0 < n_c; j0 += 32) {
+            const int j = j0 + lane;
+            const int pos = j < n_c ? at(j) : 0;
+            const double I = j < n_c ? s_I[pos] : __longlong_as_double(0x7ff8000000000000ll);
+            const bool keep = cut_off ? I == I : I > cut;
+            const int gi = keep ? s_cand[pos] : 0;
+            const Refined e = refine_eval<MODEL, false>(p, m, keep, gi, lane, s_cos);
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            const int slot = offset + __popc(mask & ((1u << lane) - 1u));
+            if (keep && slot < p.cap) {
+                const size_t o = (size_t)rot * p.cap + slot;
+                p.xyz[3 * o + 0] = e.x;
+                p.xyz[3 * o + 1] = e.y;
+                p.xyz[3 * o + 2] = e.z;
+                p.intensity[o] = I;
+                p.g_index[o] = gi;
+                if (p.exc) p.exc[o] = e.s;
+            }
+            offset += __popc(mask);
+        }
+        if (threadIdx.x == 0) p.count[rot] = min(total_keep, p.cap);
     }
     local_max_count = warp_max(local_max_count);
     if (lane == 0 && local_max_count > 0) atomicMax(p.max_count, local_max_count);
@@ -598,12 +866,53 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     if (precession_rad != 0.0 && shape_model != DS_SHAPE_LORENTZIAN_PRECESSION &&
         shape_model != DS_SHAPE_NONE_RETURN_S && shape_model != DS_SHAPE_BINARY)
         p.n_quad = (shape_model == DS_SHAPE_LORENTZIAN || shape_model == DS_SHAPE_ATANC) ? 2048 : 8192;
-    const size_t smem = (size_t)tile_g * 16 * (n_tiles > 1 ? 2 : 1) + (size_t)p.n_quad * 8;
+    const int tile_alloc = lines ? tile_g : ((tile_g + 127) & ~127);
+    const size_t smem = (size_t)tile_alloc * 16 * (n_tiles > 1 ? 2 : 1) + (size_t)p.n_quad * 8;
     // Few rotations over a large table (one warp per rotation cannot fill 148 SMs): smaller CTAs spread the rotations
     // over more SMs; the table is then streamed by more CTAs, which L2 absorbs.  sim_split = 1 / 2 / 4 / 8 forces the
     // warps per CTA.
     // Measured on the 113 082-row table (tools/bench_k12_large.py): 512 rotations 351 / 308 / 488 us with 8 / 2 / 1 warps
     // per CTA, 2 048 rotations 428 / 993 / 1535 us.
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Few rotations over a large table: one CTA per rotation, the table split across its warps (simulate_cta_kernel).
+    // Measured on the 113 082-row table (tools/bench_k12_large.py), CTA per rotation vs warp per rotation: 128 rotations
+    // 98 vs 322 us, 512: 125 vs 333 us, 1 024: 182 vs 359 us, 2 048: 1 122 vs 405 us (the CTAs no longer run in step and
+    // every one streams the table from L2).  sim_cta = 0 never, 1 forces it; sim_stash = candidate capacity of a rotation
+    // (small values exercise the fall-back in the tests).
+    {
+        const int o = option(OPT_SIM_CTA);
+        if (!lines && n_g > 0 && (o > 0 || (o < 0 && n_g >= 4096 && n_rot <= 1024))) {
+            int stash = option(OPT_SIM_STASH);
+            if (stash < SIM_CHUNK) stash = 4096;
+            int n_chunks = (stash + SIM_CHUNK - 1) / SIM_CHUNK;
+            if (n_chunks > SIM_MAX_CHUNKS) n_chunks = SIM_MAX_CHUNKS;
+            const size_t smem_c = (size_t)n_chunks * SIM_CHUNK * 12 + (((size_t)SIM_WARPS * n_chunks + 15) & ~(size_t)15) +
+                                  (size_t)p.n_quad * 8;
+            auto launch_cta = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+                int blocks_per_sm = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, SIM_THREADS, smem_c);
+                if (blocks_per_sm < 1) blocks_per_sm = 1;
+                const int grid = n_rot < num_sms() * blocks_per_sm ? n_rot : num_sms() * blocks_per_sm;
+                kern<<<grid, SIM_THREADS, smem_c, st>>>(p, n_chunks);
+            };
+            if (precession_rad != 0.0) {
+                launch_cta(simulate_cta_kernel<-1>);
+            } else {
+                switch (shape_model) {
+                    case DS_SHAPE_BINARY: launch_cta(simulate_cta_kernel<DS_SHAPE_BINARY>); break;
+                    case DS_SHAPE_LINEAR: launch_cta(simulate_cta_kernel<DS_SHAPE_LINEAR>); break;
+                    case DS_SHAPE_SINC: launch_cta(simulate_cta_kernel<DS_SHAPE_SINC>); break;
+                    case DS_SHAPE_SIN2C: launch_cta(simulate_cta_kernel<DS_SHAPE_SIN2C>); break;
+                    case DS_SHAPE_ATANC: launch_cta(simulate_cta_kernel<DS_SHAPE_ATANC>); break;
+                    case DS_SHAPE_LORENTZIAN: launch_cta(simulate_cta_kernel<DS_SHAPE_LORENTZIAN>); break;
+                    case DS_SHAPE_NONE_RETURN_S: launch_cta(simulate_cta_kernel<DS_SHAPE_NONE_RETURN_S>); break;
+                    default: launch_cta(simulate_cta_kernel<-1>); break;  // lorentzian_precession with zero angle
+                }
+            }
+            return check_launch("ds_simulate (CTA per rotation)");
+        }
+    }
     int wpb = SIM_WARPS;
     if (n_g >= 2048 && n_rot < 1024) wpb = 2;
     {
@@ -611,7 +920,6 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         if (o == 1 || o == 2 || o == 4 || o == 8) wpb = o;
     }
     const int n_batches = (n_rot + wpb - 1) / wpb;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     // no precession: one lean kernel per shape factor model; anything with precession: the general kernel
     auto launch = [&](auto kern, int slot) {
         (void)slot;
@@ -621,7 +929,7 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, wpb * 32, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         const int grid = n_batches < num_sms() * blocks_per_sm ? n_batches : num_sms() * blocks_per_sm;
-        kern<<<grid, wpb * 32, smem, st>>>(p, n_tiles, tile_g);
+        kern<<<grid, wpb * 32, smem, st>>>(p, n_tiles, tile_g, tile_alloc);
     };
 #define DS_SIM(M, SLOT)                                   \
     do {                                                  \

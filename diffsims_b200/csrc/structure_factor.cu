@@ -234,11 +234,189 @@ structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const doubl
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// factorised phases over the index BOX (dense integer tables of large cells)
+//
+// For a fixed h and element e,  S_e[k][l] = sum_{j in e} (Ex_j[h] Ey_j[k]) Ez_j[l]  is a small complex matrix product over
+// the atoms.  A CTA takes one h, 16 values of k and 64 of l; a thread keeps a 4 (k) x 2 (l) register tile, so an atom costs
+// it six 16-byte shared loads for 32 DFMA (one complex multiply-add per pair: 4 DFMA instead of the 8 of the row kernel
+// above, and no per-pair index arithmetic) -- bound by the FP64 pipe.  Box entries that are not rows of the table cost
+// nothing when a whole warp tile (8 x 32) is empty, and are dropped at the end otherwise.  The atoms are split over up to
+// eight CTAs per tile (a 61^3 box has only ~130 live CTA tiles); every split writes its partial sums to its own box-shaped
+// scratch array and a gather pass adds them in a fixed order into the table rows (duplicates of an index triple, like
+// the second (000) the new API appends, read the same entries).
+// ---------------------------------------------------------------------------------------------------
+constexpr int SFB_MAX_H = 63;
+// atom splits of the box kernel: enough CTAs to fill the GPU for cells of a few hundred atoms, result boxes <= 64 MB
+inline int sfb_splits(int n_atoms, int H) {
+    const long long W = 2ll * H + 1, box_bytes = W * W * W * 16;
+    long long s = (n_atoms + 63) / 64;
+    if (s > 8) s = 8;
+    if (s * box_bytes > (64ll << 20)) s = (64ll << 20) / box_bytes;
+    return s < 1 ? 1 : (int)s;
+}
+constexpr int SFB_THREADS = 128;   // 4 warps: 2 (k) x 2 (l)
+constexpr int SFB_KT = 16, SFB_LT = 64;
+constexpr int SFB_ATOMS = 32;      // atoms per shared-memory tile: 32 x (16 + 64) x 16 B = 40 KB
+
+__global__ void sf_box_clear_kernel(long long n, int *__restrict__ idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = -1;
+}
+__global__ void sf_box_scatter_kernel(int n_g, const double *__restrict__ hkl, int H, int *__restrict__ idx) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_g) return;
+    const int W = 2 * H + 1;
+    const int h = (int)hkl[3 * g] + H, k = (int)hkl[3 * g + 1] + H, l = (int)hkl[3 * g + 2] + H;
+    idx[((long long)h * W + k) * W + l] = g;  // (rows sharing an index triple: any of them, they share |g|)
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(SFB_THREADS)
+structure_factor_box_kernel(const double *__restrict__ gnorm, int n_atoms, int n_elem, const int *__restrict__ elem_start,
+                            const double *__restrict__ coeffs, const double *__restrict__ dw, int H, int n_split, int n_ltiles,
+                            const double2 *__restrict__ table, const int *__restrict__ idx, double2 *__restrict__ Fbox) {
+    extern __shared__ __align__(16) unsigned char sfb_smem[];
+    double2 *s_P = reinterpret_cast<double2 *>(sfb_smem);        // [SFB_ATOMS][SFB_KT]: Ex_j[h] Ey_j[k]
+    double2 *s_Z = s_P + SFB_ATOMS * SFB_KT;                     // [SFB_ATOMS][SFB_LT]: Ez_j[l]
+    __shared__ double s_coef[SF_MAX_ELEM * 10];
+    __shared__ double s_dw[SF_MAX_ELEM];
+    __shared__ int s_start[SF_MAX_ELEM + 1];
+    const int W = 2 * H + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wk = warp >> 1, wl = warp & 1, lk = lane >> 4, ll = lane & 15;
+    const int h = blockIdx.y, k_cta = blockIdx.x * SFB_KT, l_cta = (blockIdx.z % n_ltiles) * SFB_LT;
+    // this CTA's share of the atoms (whole shared-memory tiles): the partial sums of the splits go to separate result
+    // boxes that the gather pass adds in a fixed order
+    const int split = blockIdx.z / n_ltiles;
+    const int tiles_per_split = ((n_atoms + SFB_ATOMS - 1) / SFB_ATOMS + n_split - 1) / n_split;
+    const int atom_lo = min(n_atoms, split * tiles_per_split * SFB_ATOMS);
+    const int atom_hi = min(n_atoms, atom_lo + tiles_per_split * SFB_ATOMS);
+    Fbox += (size_t)split * (size_t)(2 * H + 1) * (2 * H + 1) * (2 * H + 1);
+    // this thread's entries: k = k_cta + kq + rk (rk = 0..3), l = l_cta + lq + 16 rl (rl = 0, 1)
+    const int kq = wk * 8 + lk * 4, lq = wl * 32 + ll;
+    int row[4][2];
+    bool any = false;
+#pragma unroll
+    for (int rk = 0; rk < 4; ++rk)
+#pragma unroll
+        for (int rl = 0; rl < 2; ++rl) {
+            const int k = k_cta + kq + rk, l = l_cta + lq + 16 * rl;
+            row[rk][rl] = (k < W && l < W) ? __ldg(idx + ((long long)h * W + k) * W + l) : -1;
+            any |= row[rk][rl] >= 0;
+        }
+    const bool warp_live = __any_sync(0xffffffffu, any);
+    if (!__syncthreads_or(warp_live)) return;  // no table row in this CTA's part of the box
+    for (int i = tid; i < n_elem * 10; i += SFB_THREADS) s_coef[i] = coeffs[i];
+    for (int i = tid; i < n_elem; i += SFB_THREADS) s_dw[i] = dw[i];
+    for (int i = tid; i <= n_elem; i += SFB_THREADS) s_start[i] = elem_start[i];
+    double g2[4][2], Fre[4][2], Fim[4][2];
+#pragma unroll
+    for (int rk = 0; rk < 4; ++rk)
+#pragma unroll
+        for (int rl = 0; rl < 2; ++rl) {
+            const double gn = row[rk][rl] >= 0 ? __ldg(gnorm + row[rk][rl]) : 0.0;
+            g2[rk][rl] = gn * gn;
+            Fre[rk][rl] = Fim[rk][rl] = 0.0;
+        }
+    __syncthreads();
+    const double2 *tab_x = table, *tab_y = table + (size_t)n_atoms * W, *tab_z = table + 2 * (size_t)n_atoms * W;
+
+    for (int e = 0; e < n_elem; ++e) {
+        const int e_lo = max(s_start[e], atom_lo), e_hi = min(s_start[e + 1], atom_hi);
+        if (e_lo >= e_hi) continue;  // (uniform) none of this element's atoms in this split
+        double re[4][2], im[4][2];
+#pragma unroll
+        for (int rk = 0; rk < 4; ++rk)
+#pragma unroll
+            for (int rl = 0; rl < 2; ++rl) re[rk][rl] = im[rk][rl] = 0.0;
+        for (int base = e_lo; base < e_hi; base += SFB_ATOMS) {
+            const int n_tile = min(SFB_ATOMS, e_hi - base);
+            __syncthreads();  // the previous tile has been consumed
+            for (int i = tid; i < n_tile * SFB_KT; i += SFB_THREADS) {
+                const int j = i / SFB_KT, k = k_cta + i % SFB_KT;
+                double2 v = make_double2(0.0, 0.0);
+                if (k < W) {
+                    const double2 ex = __ldg(tab_x + (size_t)(base + j) * W + h), ey = __ldg(tab_y + (size_t)(base + j) * W + k);
+                    v = make_double2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
+                }
+                s_P[i] = v;
+            }
+            for (int i = tid; i < n_tile * SFB_LT; i += SFB_THREADS) {
+                const int j = i / SFB_LT, l = l_cta + i % SFB_LT;
+                s_Z[i] = l < W ? __ldg(tab_z + (size_t)(base + j) * W + l) : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            if (!warp_live) continue;  // (warp-uniform; the barriers above are still taken)
+            for (int j = 0; j < n_tile; ++j) {
+                const double2 *pr = s_P + j * SFB_KT + kq, *zr = s_Z + j * SFB_LT + lq;
+                const double2 z0 = zr[0], z1 = zr[16];
+#pragma unroll
+                for (int rk = 0; rk < 4; ++rk) {
+                    const double2 a = pr[rk];
+                    re[rk][0] = fma(a.x, z0.x, re[rk][0]);
+                    re[rk][0] = fma(-a.y, z0.y, re[rk][0]);
+                    im[rk][0] = fma(a.x, z0.y, im[rk][0]);
+                    im[rk][0] = fma(a.y, z0.x, im[rk][0]);
+                    re[rk][1] = fma(a.x, z1.x, re[rk][1]);
+                    re[rk][1] = fma(-a.y, z1.y, re[rk][1]);
+                    im[rk][1] = fma(a.x, z1.y, im[rk][1]);
+                    im[rk][1] = fma(a.y, z1.x, im[rk][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int rk = 0; rk < 4; ++rk)
+#pragma unroll
+            for (int rl = 0; rl < 2; ++rl) {
+                if (row[rk][rl] < 0) continue;
+                // f_e(g^2) * exp(-g^2 B_e / 4): the real part of the reference's complex exponent (sim_utils.py:297-301)
+                const double fe = scattering_factor<MODEL>(g2[rk][rl], &s_coef[e * 10]) * exp(-0.25 * g2[rk][rl] * s_dw[e]);
+                Fre[rk][rl] = fma(fe, re[rk][rl], Fre[rk][rl]);
+                Fim[rk][rl] = fma(fe, im[rk][rl], Fim[rk][rl]);
+            }
+    }
+#pragma unroll
+    for (int rk = 0; rk < 4; ++rk)
+#pragma unroll
+        for (int rl = 0; rl < 2; ++rl) {
+            if (row[rk][rl] < 0) continue;
+            const int k = k_cta + kq + rk, l = l_cta + lq + 16 * rl;
+            Fbox[((long long)h * W + k) * W + l] = make_double2(Fre[rk][rl], Fim[rk][rl]);
+        }
+}
+
+__global__ void sf_box_gather_kernel(int n_g, const double *__restrict__ hkl, int H, int n_split, const double2 *__restrict__ Fbox,
+                                     const double *__restrict__ prefactor, double *__restrict__ F_out, double *__restrict__ I_out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_g) return;
+    const int W = 2 * H + 1;
+    const int h = (int)hkl[3 * g] + H, k = (int)hkl[3 * g + 1] + H, l = (int)hkl[3 * g + 2] + H;
+    double2 F = make_double2(0.0, 0.0);
+    for (int s = 0; s < n_split; ++s) {  // fixed order: reproducible sums
+        const double2 part = Fbox[(size_t)s * W * W * W + ((long long)h * W + k) * W + l];
+        F.x += part.x;
+        F.y += part.y;
+    }
+    if (F_out) {
+        F_out[2 * g] = F.x;
+        F_out[2 * g + 1] = F.y;
+    }
+    if (I_out) {
+        const double p = prefactor ? prefactor[g] : 1.0;
+        I_out[g] = p * (F.x * F.x + F.y * F.y);  // sim_utils.py:353
+    }
+}
+
 }  // namespace ds
 
 extern "C" int64_t ds_structure_factors_scratch_bytes(int32_t n_atoms, int32_t hkl_int_max) {
     if (n_atoms < 0 || hkl_int_max < 0) return -1;
-    return 3ll * n_atoms * (2ll * hkl_int_max + 1) * 16;
+    const long long W = 2ll * hkl_int_max + 1;
+    // phase-factor tables | (box kernel, H <= 63) index box (int32) | result box (complex128)
+    long long bytes = 3ll * n_atoms * W * 16;
+    if (hkl_int_max <= ds::SFB_MAX_H) bytes += ((W * W * W * 4 + 15) & ~15ll) + ds::sfb_splits(n_atoms, hkl_int_max) * W * W * W * 16;
+    return bytes;
 }
 
 extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl, const double *gnorm,
@@ -262,6 +440,33 @@ extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl
         double2 *table = static_cast<double2 *>(table_scratch);
         const long long n_tab = 3ll * n_atoms * W;
         sf_phase_table_kernel<<<(unsigned)((n_tab + 255) / 256), 256, 0, st>>>(n_atoms, H, frac, occ, table);
+        // tables that fill a good part of their index box: the register-tiled box kernel
+        const long long box = (long long)W * W * W;
+        if (H <= SFB_MAX_H && box <= 16ll * n_g) {
+            unsigned char *after = static_cast<unsigned char *>(table_scratch) + n_tab * 16;
+            int *idx = reinterpret_cast<int *>(after);
+            double2 *Fbox = reinterpret_cast<double2 *>(after + ((box * 4 + 15) & ~15ll));
+            sf_box_clear_kernel<<<(unsigned)((box + 255) / 256), 256, 0, st>>>(box, idx);
+            sf_box_scatter_kernel<<<(n_g + 255) / 256, 256, 0, st>>>(n_g, hkl, H, idx);
+            const int n_split = sfb_splits(n_atoms, H), n_ltiles = (W + SFB_LT - 1) / SFB_LT;
+            const dim3 grid_b((W + SFB_KT - 1) / SFB_KT, W, n_ltiles * n_split);
+            const size_t smem_b = (size_t)SFB_ATOMS * (SFB_KT + SFB_LT) * 16;
+#define DS_SFB_LAUNCH(M)                                                                                                     \
+    do {                                                                                                                     \
+        cudaFuncSetAttribute(structure_factor_box_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);        \
+        structure_factor_box_kernel<M><<<grid_b, SFB_THREADS, smem_b, st>>>(gnorm, n_atoms, n_elem, elem_start, coeffs, dw, H, \
+                                                                            n_split, n_ltiles, table, idx, Fbox);            \
+    } while (0)
+            if (scattering_model == DS_SCATT_LOBATO)
+                DS_SFB_LAUNCH(DS_SCATT_LOBATO);
+            else if (scattering_model == DS_SCATT_XTABLES)
+                DS_SFB_LAUNCH(DS_SCATT_XTABLES);
+            else
+                DS_SFB_LAUNCH(DS_SCATT_NONE);
+#undef DS_SFB_LAUNCH
+            sf_box_gather_kernel<<<(n_g + 255) / 256, 256, 0, st>>>(n_g, hkl, H, n_split, Fbox, prefactor, F_out, I_out);
+            return check_launch("ds_structure_factors (box)");
+        }
         const int grid_t = (n_g + SFT_G_TILE - 1) / SFT_G_TILE;
 #define DS_SFT_LAUNCH(M)                                                                                                   \
     do {                                                                                                                   \

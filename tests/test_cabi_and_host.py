@@ -43,7 +43,10 @@ def test_abi_argument_validation_without_gpu():
     rc = lib.ds_structure_factors(None, 4, None, None, 1, None, None, 1, None, None, None, 7, None, None, None, 0, None)
     assert rc != 0 and b"scattering" in lib.ds_last_error()
     assert lib.ds_set_option(b"no_such_option", 1) != 0 and b"unknown option" in lib.ds_last_error()
-    assert lib.ds_render_scratch_bytes(1000, 32) == 16 + 1000 * 432      # 32 + 8 cap + 4 cap + 8 ceil(cap / 16), 16-aligned
+    # per template the larger of the two tcgen05 record layouts: 32 + 8 cap + 4 cap + 8 ceil(cap / 16) (per-reflection
+    # kernel) and 32 + 8 cap + 528 (row-binned kernel: row offsets), 16-aligned
+    assert lib.ds_render_scratch_bytes(1000, 32) == 16 + 1000 * 816
+    assert lib.ds_render_scratch_bytes(1000, 992) == 16 + 1000 * 12432
     assert lib.ds_structure_factors_scratch_bytes(500, 30) == 3 * 500 * 61 * 16
     assert lib.ds_render_launch_count(32, 256, 256, 40, 1, 3.8) == 1 and lib.ds_render_launch_count(288, 256, 256, 40, 1, 177.0) == 2
     assert lib.ds_render_launch_count(288, 512, 512, 40, 1, 177.0) == 1    # larger than a tensor-memory template: float32 kernels

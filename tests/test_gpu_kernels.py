@@ -38,6 +38,40 @@ def test_structure_factors(eng, name, sp, aligned):
     np.testing.assert_allclose(I.cpu().numpy(), np.abs(ref) ** 2, rtol=1e-9, atol=1e-20 * scale ** 2)
 
 
+@pytest.mark.parametrize("sp", ["lobato", "xtables", None])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_structure_factors_factorised_kernels_match_the_direct_kernel(eng, sp, sparse):
+    """Large cells with integer indices take the factorised kernels (phase tables per atom and axis; the box kernel
+    register-tiles the index box, the row kernel handles sparse tables): both agree with the direct sincospi kernel to
+    float64 round-off, rows that share an index triple (the second (000) of the new API) included."""
+    import torch
+    from diffsims_b200 import _cabi
+    st = cases.phase("large").structure
+    gs = K.GSet(st, 1.2, True)
+    hkl = np.vstack([gs.hkl_int, [0, 0, 0], [1, -2, 3]])
+    if sparse:  # a sparse table in a big box: every other row, and one far index -> the row kernel
+        hkl = np.vstack([hkl[::2], [40, 0, 0]])
+    assert len(hkl) >= 4096
+    g = st.lattice.rnorm(hkl)
+    dev = eng.device()
+    atoms = eng.AtomTable(st, cases.DW, sp, dev)
+    hkl_d, g_d = torch.as_tensor(hkl.astype(float), device=dev), torch.as_tensor(g, device=dev)
+    pre = torch.as_tensor(np.linspace(0.5, 2.0, len(hkl)), device=dev)
+    out = {}
+    for name, H in (("direct", 0), ("factorised", int(np.abs(hkl).max()))):
+        F = torch.zeros((len(hkl), 2), dtype=torch.float64, device=dev)
+        I = torch.zeros((len(hkl),), dtype=torch.float64, device=dev)
+        scratch = None
+        if H:
+            scratch = torch.empty(int(_cabi.lib().ds_structure_factors_scratch_bytes(atoms.n_atoms, H)), dtype=torch.uint8, device=dev)
+        eng.launch_structure_factors(atoms, hkl_d, g_d, pre, F, I, hkl_int_max=H, scratch=scratch)
+        out[name] = (F.cpu().numpy(), I.cpu().numpy())
+    scale = np.abs(out["direct"][0]).max()
+    np.testing.assert_allclose(out["factorised"][0], out["direct"][0], rtol=1e-9, atol=1e-11 * scale)
+    np.testing.assert_allclose(out["factorised"][1], out["direct"][1], rtol=1e-9, atol=1e-20 * scale ** 2)
+    assert not np.array_equal(out["factorised"][0], out["direct"][0])   # (a different kernel did run)
+
+
 # --------------------------------------------------------------------------- K2
 def _gtable_new_api(eng, phase, rr, with_direct_beam, sp="lobato", dw=None):
     st = phase.structure
@@ -157,6 +191,42 @@ def test_simulate_scan_line_cull_is_identical(eng, opts, name, rr, s_max, model,
             assert np.allclose(x, y, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(x).max())), (r, field)
 
 
+@pytest.mark.parametrize("name,rr,s_max,model,prec_deg,min_int", [
+    ("large", 1.2, 0.01, "lorentzian", 0.0, 1e-20),
+    ("large", 1.2, 0.02, "linear", 0.0, 1e-3),
+    ("si", 2.0, 0.05, "sinc", 0.0, 1e-20),
+    ("graphite", 2.0, 0.1, "binary", 0.0, -1.0),
+    ("si", 2.0, 0.01, "lorentzian_precession", 0.5, 1e-20),
+    ("si", 1.5, 0.02, "sin2c", 0.3, 1e-20),      # numerically averaged precession: warp-cooperative evaluation
+    ("triclinic", 1.5, 0.02, "return_s", 0.0, 1e-20),  # excitation errors returned, no intensity cut
+])
+def test_simulate_cta_per_rotation_is_identical(eng, opts, name, rr, s_max, model, prec_deg, min_int):
+    """simulate_cta_kernel (few rotations over a large table: one CTA per rotation, the table split across its warps)
+    returns exactly the reflection lists of the one-warp-per-rotation kernel -- with its default candidate stash, with a
+    pool of a few chunks (some rotations fit, some do not) and through its fall-back alone (a single 64-entry chunk)."""
+    phase = cases.phase(name)
+    gs, gt = _gtable_new_api(eng, phase, rr, True)
+    wl = K.get_electron_wavelength(200)
+    q = random_quats(37, 5)
+    q[0] = (1, 0, 0, 0)
+    q[1] = (np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0)
+    kw = dict(precession_rad=np.deg2rad(prec_deg), want_exc=True, min_intensity=min_int)
+    opts(sim_lines=0, sim_cta=0)
+    ref = eng.simulate(gt, q, wl, s_max, s_max, model, **kw)
+    assert int(ref.count.sum()) > 0
+    for cta, stash in ((1, -1), (1, 512), (1, 64)):
+        opts(sim_cta=cta, sim_stash=stash)
+        got = eng.simulate(gt, q, wl, s_max, s_max, model, cap=ref.cap, **kw)
+        assert int(got.max_count) == int(ref.max_count), (cta, stash)
+        assert np.array_equal(got.count.cpu().numpy(), ref.count.cpu().numpy()), (cta, stash)
+        for r in range(len(q)):
+            n = int(ref.count[r])
+            assert np.array_equal(got.g_index[r, :n].cpu().numpy(), ref.g_index[r, :n].cpu().numpy()), (cta, stash, r)
+            for field in ("xyz", "intensity", "exc"):  # separate instantiations: fma contraction may differ
+                x, y = getattr(ref, field)[r, :n].cpu().numpy(), getattr(got, field)[r, :n].cpu().numpy()
+                assert np.allclose(x, y, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(x).max())), (cta, stash, r, field)
+
+
 def test_simulate_cap_overflow_retry(eng):
     phase = cases.phase("si")
     gs, gt = _gtable_new_api(eng, phase, 5.0, True)
@@ -258,14 +328,16 @@ def test_render_graphite_golden(eng, golden_dir):
 
 
 # --------------------------------------------------------------------------- K3 schedule variants
-@pytest.mark.parametrize("variant", ["umma", "umma_nowin", "pipe", "pipe_tma", "G8", "G4", "G2", "G1"])
+@pytest.mark.parametrize("variant", ["umma", "umma_nowin", "rows", "pipe", "pipe_tma", "G8", "G4", "G2", "G1"])
 @pytest.mark.parametrize("shape,sigma", [((256, 256), 10.0), ((144, 144), 3.0), ((90, 130), 2.0)])
 def test_render_schedule_variants_agree_with_oracle(eng, opts, variant, shape, sigma):
     """The tcgen05 kernel, the warp-specialised pipelined kernel and every group size of the phase-synchronous
     kernel against the oracle (130 is not a multiple of 4: scalar-store instantiation)."""
     import torch
-    if variant.startswith("umma"):
-        opts(render_group=-1, render_umma=1, render_umma_window=0 if variant == "umma_nowin" else -1)
+    if variant == "rows":     # the row-binned banded product (render_rows.cu)
+        opts(render_group=-1, render_umma=1, render_rows=1)
+    elif variant.startswith("umma"):
+        opts(render_group=-1, render_umma=1, render_rows=0, render_umma_window=0 if variant == "umma_nowin" else -1)
     elif variant.startswith("pipe"):   # all-zero regions by st.global (default) or by TMA store (option; measured slower)
         opts(render_group=-1, render_pipe=1, render_umma=0, render_zero_tma=1 if variant == "pipe_tma" else -1)
     else:
@@ -340,7 +412,7 @@ def test_render_slow_path_with_many_spots(eng):
         assert np.abs(out[r] - ref).max() <= IMG_ATOL * max(ref.max(), 1.0)
 
 
-@pytest.mark.parametrize("pipe", ["umma", "1", "0"])
+@pytest.mark.parametrize("pipe", ["umma", "rows", "1", "0"])
 @pytest.mark.parametrize("cap,sigma,normalize,shape", [
     (288, 10.0, True, (256, 256)), (288, 3.0, False, (256, 256)), (512, 6.0, True, (256, 256)),
     (1024, 2.0, True, (256, 256)), (288, 7.0, True, (96, 200)), (160, 5.0, True, (100, 150)),
@@ -351,8 +423,8 @@ def test_render_fast_path_with_many_spots(eng, opts, pipe, cap, sigma, normalize
     shared memory) and render_kernel for everything else.  The tensor-core paths use bf16 x 3 split products,
     incl. reflect images at the borders, partial tiles and rows that are not 16-byte multiples."""
     import torch
-    if pipe == "umma":
-        opts(render_umma=1)
+    if pipe in ("umma", "rows"):
+        opts(render_umma=1, render_rows=int(pipe == "rows"))
     else:
         opts(render_umma=0, render_pipe=int(pipe))
     rng = np.random.default_rng(cap)
@@ -391,11 +463,14 @@ def test_render_tensor_path_accuracy(eng, opts):
     args = (cnt, torch.as_tensor(X, device=eng.device()), torch.as_tensor(I, device=eng.device()), shape, 10.0,
             1 / 128, (127.5, 127.5))
     out = {}
-    for name, kw in (("umma", dict(render_umma=1)), ("mma", dict(render_umma=0, render_mma=1)),
-                     ("fma", dict(render_umma=0, render_mma=0))):
+    for name, kw in (("umma", dict(render_umma=1, render_rows=0, render_umma_team=4)),
+                     ("umma2", dict(render_umma=1, render_rows=0, render_umma_team=2)), ("rows", dict(render_umma=1, render_rows=1)),
+                     ("mma", dict(render_umma=0, render_mma=1)), ("fma", dict(render_umma=0, render_mma=0))):
         opts(**kw)
         out[name] = eng.render(*args).cpu().numpy()
-    for name in ("umma", "mma"):
+    # two or four producer warps per operand stage: the same operands, the same products
+    assert np.array_equal(out["umma"], out.pop("umma2"))
+    for name in ("umma", "rows", "mma"):
         assert not np.array_equal(out[name], out["fma"])            # the tensor-core path did run
         assert np.abs(out[name] - out["fma"]).max() < 3e-5, name
     assert all(o[r].max() == 1.0 for o in out.values() for r in range(n))

@@ -1,5 +1,5 @@
 """K1 / K2 on the large-cell config (BASELINE configs[3]): factorised vs direct structure factors, K2 per-rotation cost
-for few and many rotations (warps per CTA chosen by the launcher vs forced).   python tools/bench_k12_large.py"""
+for few and many rotations (one warp per rotation with 8 / 2 warps per CTA, one CTA per rotation).   python tools/bench_k12_large.py"""
 import sys
 
 import numpy as np
@@ -46,12 +46,16 @@ print(f"K1 large cell ({b.gtable.n} g x 500 atoms, incl. table packing): factori
 
 q_all = torch.as_tensor(active_quaternions(random_quats(16384, 0)), device=dev)
 b.calibrate_cap(q_all[:2048])
-for n in (512, 2048, 16384):
+VARIANTS = [("auto", dict(sim_cta=-1, sim_split=-1)), ("warp/rot x8", dict(sim_cta=0, sim_split=8)),
+            ("warp/rot x2", dict(sim_cta=0, sim_split=2)), ("CTA/rot", dict(sim_cta=1, sim_split=-1))]
+for n in (128, 512, 1024, 2048, 16384):
     q = q_all[:n].contiguous()
     line = f"K2 large cell n_rot={n:6d}:"
-    for split in (-1, 8, 2, 1):
-        _cabi.set_option("sim_split", split)
+    for name, kw in VARIANTS:
+        for k, v in kw.items():
+            _cabi.set_option(k, v)
         t = timeit(lambda: b.simulate(q), n=5)
-        line += f"  warps/CTA {'auto' if split < 0 else split}: {t * 1e3:8.1f} us = {t * 1e6 / n:7.1f} ns/rot ({n * b.gtable.n / t / 1e6:6.1f} G rows/s)"
-    _cabi.set_option("sim_split", -1)
+        line += f"  {name}: {t * 1e3:8.1f} us = {t * 1e6 / n:6.1f} ns/rot"
+    for k in ("sim_cta", "sim_split"):
+        _cabi.set_option(k, -1)
     print(line, flush=True)

@@ -1,6 +1,6 @@
 """K3 variants over the BASELINE.json configs (device-resident spot tables, CUDA events).
     python tools/bench_k3_variants.py [n_rot]
-For each configuration: the tcgen05 kernel (with and without per-chunk column windows) against the float32 /
+For each configuration: the two tcgen05 kernels (per-reflection rank-S product, row-binned banded product) against the float32 /
 mma.sync kernels of round 1, as a fraction of the measured copy peak (MEASURED_PEAKS.json hbm_gbs)."""
 import json
 import sys
@@ -49,9 +49,9 @@ CONFIGS = [
     ("C5 Fe3C rr2 s.05", "fe3c", 200, 2.0, 0.05, 10.0, 0.5),
     ("C4 large rr2.5 s.01", "large", 200, 2.5, 0.01, 10.0, 1 / 8),
 ]
-VARIANTS = [("tcgen05", dict(render_umma=1, render_umma_window=-1)),
-            ("tcgen05 no-window", dict(render_umma=1, render_umma_window=0)),
-            ("round-1 kernels", dict(render_umma=0, render_umma_window=-1))]
+VARIANTS = [("tcgen05 per-spot", dict(render_umma=1, render_rows=0)),
+            ("tcgen05 rows", dict(render_umma=1, render_rows=1)),
+            ("float32 kernels", dict(render_umma=0, render_rows=-1))]
 dev = engine.device()
 only = sys.argv[2] if len(sys.argv) > 2 else None
 for name, ph, kv, rr, s_max, sigma, scale in CONFIGS:
@@ -81,6 +81,6 @@ for name, ph, kv, rr, s_max, sigma, scale in CONFIGS:
             ref = got
         else:
             line += f" dmax {float((got - ref).abs().max()):.1e} |"
-    for k in ("render_umma", "render_umma_window"):
+    for k in ("render_umma", "render_rows"):
         _cabi.set_option(k, -1)
     print(line, flush=True)
