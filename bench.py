@@ -345,6 +345,15 @@ def config_probe(name, dev, peak, n=None):
                         k2_mrot_per_s=n_t / (k2 * 1e-3) / 1e6, k2_g_rows_per_s=n_t * b.gtable.n / (k2 * 1e-3),
                         k3_gbs=gbs, k3_frac=gbs / peak, k3_kernels=engine.render_launch_count(b.cap, b.shape, b.sigma, True, b.mean_spots),
                         templates_per_s=n_t / ((k1 + k2 + k3) * 1e-3), spot_lists_only_templates_per_s=n_t / (spots_ms * 1e-3)))
+        if b.gtable.n >= 4096:
+            # K2 over a large table: a launch of few rotations (one CTA per rotation, the table split across its warps)
+            # against the warp-per-rotation kernel at scale
+            q_big = torch.as_tensor(active_quaternions(random_quats(16384, 9)), device=dev)
+            few = _time_ms(lambda: b.simulate(q_big[:512]))
+            many = _time_ms(lambda: b.simulate(q_big))
+            out[-1]["k2_large_table"] = dict(ns_per_rotation_512=few * 1e6 / 512, ns_per_rotation_16384=many * 1e6 / 16384,
+                                             ratio=(few / 512) / (many / 16384))
+            del q_big
         del img, sp, q
         torch.cuda.empty_cache()
     return out

@@ -37,6 +37,7 @@ static const OptDef g_defs[OPT_COUNT] = {
     {"render_zero_tma", "DS_RENDER_ZERO_TMA"},
     {"render_umma_team", "DS_RENDER_UMMA_TEAM"},
     {"render_rows", "DS_RENDER_ROWS"},
+    {"render_rows_stages", "DS_RENDER_ROWS_STAGES"},
     {"sim_lines", "DS_SIM_LINES"},
     {"sim_split", "DS_SIM_SPLIT"},
     {"sim_cta", "DS_SIM_CTA"},

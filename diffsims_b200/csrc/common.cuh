@@ -27,6 +27,7 @@ enum Opt {
     OPT_RENDER_ZERO_TMA,
     OPT_RENDER_UMMA_TEAM,
     OPT_RENDER_ROWS,
+    OPT_RENDER_ROWS_STAGES,
     OPT_SIM_LINES,
     OPT_SIM_SPLIT,
     OPT_SIM_CTA,

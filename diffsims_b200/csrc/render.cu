@@ -498,8 +498,11 @@ extern "C" int ds_render(void *stream, int32_t n_tmpl, int32_t cap, const int32_
     // float32 pipelined kernel wins below ~16 reflections per template (sigma 10), the tcgen05 kernel above.
     if (fast && !wide && !g_forced) {
         if (wants_umma(cap, mean_spots_hint)) {
-            // render_rows = 1: the row-binned banded product (render_rows.cu) instead of the per-reflection one
-            if (option(OPT_RENDER_ROWS) == 1) {
+            // Very dense templates take the row-binned banded product (render_rows.cu), whose cost barely depends on the
+            // number of reflections; measured cross-over against the per-reflection product at ~320 reflections per
+            // template (sigma 10; profiles/r02_k3_variants_v8.txt).  render_rows = 0 / 1 forces it off / on.
+            const int ro = option(OPT_RENDER_ROWS);
+            if (ro >= 0 ? ro != 0 : (mean_spots_hint > 0.0 ? mean_spots_hint >= 320.0 : cap >= 640)) {
                 const int rc = launch_render_rows(p, static_cast<unsigned char *>(scratch) + 16, st);
                 if (rc != 0) return rc < 0 ? rc : 0;
             }

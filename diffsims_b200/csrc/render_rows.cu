@@ -9,15 +9,17 @@
 //   * K runs over EXTENDED ROWS e = r + RP (RP = radius rounded up to 16), 16 at a time; a chunk of 16 rows is skipped when
 //     none of them holds a reflection (sparse templates touch a few chunks only);
 //   * B = P_ext chunk (16 x W), written ONCE per chunk to shared memory as bf16 high and low parts (MN-major, no swizzle)
-//     by the producer warps: a lane owns one row and eight 8-pixel units and sums the row's reflections in float32;
+//     by sixteen producer warps, one row each: lane = 8-pixel unit, the row's reflections are summed in float32 in a
+//     warp-uniform loop, and the row is computed BEFORE the warp waits for the stage to be free;
 //   * A = G[y - r] (128 x 16) never changes: every (half, chunk) pair reads a window of ONE master operand
 //     M[yy][k] = G[yy - k] that sits in shared memory for the CTA's lifetime -- the window's first row 128 h + RP - 16 c
 //     is a multiple of 16, i.e. a whole number of 8-row core matrices, so it is only an address in the descriptor;
 //   * a chunk feeds both halves of the template where its rows reach both (two accumulators of 256 columns in tensor
 //     memory), three products per (half, chunk): A_hi B_hi + A_hi B_lo + A_lo B_hi (float32 accumulation);
 //   * a half that no chunk reaches is zeroed by one product with an all-zero window of the master.
-// Front warp, epilogue (tcgen05.ld -> max -> scale -> swizzled staging -> TMA store), slots and barriers are those of
-// render_umma.cu; the per-template records come from render_prepare_rows_kernel below (float64 projection, ordering by
+// 28 warps: front, MMA issue, 16 producers (one per row of a chunk), 8 epilogue; setmaxnreg gives the epilogue warpgroups
+// 112 registers and everyone else 48.  Front warp, epilogue (tcgen05.ld -> max -> scale -> swizzled staging -> TMA store),
+// slots and barriers are those of render_umma.cu; the per-template records come from render_prepare_rows_kernel below (float64 projection, ordering by
 // row with ties in list order, "last write wins" inside a pixel, row offsets, mask of the non-empty chunks).
 //
 // Reference: diffsims/pattern/detector_functions.py:293-300, diffsims/simulations/simulation2d.py:261-285, :422-441.
@@ -25,16 +27,40 @@
 
 namespace ds {
 
-constexpr int RW_NP = 3;                          // B stages = producer teams (two warps each: K groups 0 / 1)
+constexpr int RW_NP_MAX = 6;                      // B stages (chunks in flight between the producers and the tensor core): 3 .. 6
 constexpr int RW_EPI = 8;                         // epilogue warps: two per tensor-memory lane quarter
-constexpr int RW_WARPS = 2 + RW_EPI + 2 * RW_NP;  // 16
+constexpr int RW_PROD = 16;                       // producer warps: one per row of a chunk, all on the same chunk
+constexpr int RW_WARPS = 28;                      // seven warpgroups; warps 26, 27 only fill the last one
 constexpr int RW_THREADS = RW_WARPS * 32;
-constexpr int RW_EPI_WARP0 = 4;                   // warps: 0 front, 1 MMA issue, 4-11 epilogue, 2-3 and 12-15 producers
-constexpr int RW_B_BYTES = 256 * 16 * 2;          // one of B_hi / B_lo: 32 N groups x 2 K groups x 128 B
-constexpr int RW_STAGE_BYTES = 2 * RW_B_BYTES;    // 16 KB
+constexpr int RW_EPI_WARP0 = 4;                   // warps: 0 front, 1 MMA issue, 4-11 epilogue, 2-3 and 12-25 producers
+// B operand in shared memory: 8 x 8 core matrices of 128 contiguous bytes (row k of the K group at 16 k: eight
+// consecutive pixels), core matrices of consecutive 8-pixel groups 144 bytes apart -- the 16 bytes of padding spread a
+// warp's store of ONE row (lane = pixel group) over all banks; with the natural 128-byte pitch it is a 32-way conflict
+constexpr int RW_SBO = 144;
+constexpr int RW_LBO = 32 * RW_SBO;               // K groups (rows 0-7 / 8-15 of a chunk)
+constexpr int RW_B_BYTES = 2 * RW_LBO;            // one of B_hi / B_lo
+constexpr int RW_STAGE_BYTES = 2 * RW_B_BYTES;    // 18 KB
 constexpr int RW_TILE_BYTES = 32 * 32 * 4;
 constexpr int RW_SLOTS = 4;
 constexpr int RW_MAX_CAP = 2048;
+
+#ifdef DS_PROF
+// per-role cycle counters of CTA 0 (profiling builds only): [role][0] = cycles in the role's loop, [1 + i] = cycles in wait i
+__device__ unsigned long long g_rw_prof[4][4];
+#define RPROF_DECL long long rp_t0 = clock64(), rp_w[3] = {0, 0, 0}, rp_s = 0
+#define RPROF_BEGIN rp_s = clock64()
+#define RPROF_END(i) rp_w[i] += clock64() - rp_s
+#define RPROF_DONE(role)                                                                 \
+    if (blockIdx.x == 0 && lane == 0) {                                                  \
+        g_rw_prof[role][0] = (unsigned long long)(clock64() - rp_t0);                    \
+        for (int i_ = 0; i_ < 3; ++i_) g_rw_prof[role][1 + i_] = (unsigned long long)rp_w[i_]; \
+    }
+#else
+#define RPROF_DECL
+#define RPROF_BEGIN
+#define RPROF_END(i)
+#define RPROF_DONE(role)
+#endif
 
 struct RowsHeader {  // 32 bytes at the start of a record / slot
     int t, n_live;
@@ -204,11 +230,12 @@ static int launch_render_prepare_rows(const RenderParams &p, unsigned char *reco
 // ---------------------------------------------------------------------------------------------------
 // the render kernel
 // ---------------------------------------------------------------------------------------------------
+template <int RW_NP>
 __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const RenderParams p, const __grid_constant__ CUtensorMap tmap,
                                                                      const unsigned char *records, const int slot_bytes,
                                                                      const int epi_bufs) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_slot_full[RW_SLOTS], s_slot_empty[RW_SLOTS], s_stage_full[RW_NP], s_stage_empty[RW_NP],
+    __shared__ __align__(8) uint64_t s_slot_full[RW_SLOTS], s_slot_empty[RW_SLOTS], s_stage_full[RW_NP_MAX], s_stage_empty[RW_NP_MAX],
         s_half_full[2], s_half_empty[2];
     __shared__ float s_emax[2][RW_EPI];
     __shared__ uint32_t s_tmem;
@@ -246,14 +273,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
             s_norm = part;
             for (int s = 0; s < RW_SLOTS; ++s) {
                 mbar_init(&s_slot_full[s], 1);
-                mbar_init(&s_slot_empty[s], 1 + RW_EPI + 2 * RW_NP);
+                mbar_init(&s_slot_empty[s], 1 + RW_EPI + RW_PROD);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&s_half_full[s], 1);
                 mbar_init(&s_half_empty[s], RW_EPI);
             }
             for (int s = 0; s < RW_NP; ++s) {
-                mbar_init(&s_stage_full[s], 2);
+                mbar_init(&s_stage_full[s], RW_PROD);
                 mbar_init(&s_stage_empty[s], 1);
             }
             fence_mbar_init();
@@ -287,20 +314,31 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
     __syncthreads();
     const uint32_t tm = s_tmem;
 
+    // Role dispatch.  The kernel starts with 72 registers per thread (896 threads); the two epilogue warpgroups (warps
+    // 4..11) raise their allowance to 112 and every other warpgroup lowers it to 48 (an increase can only draw on what the
+    // CTA's own warps released) -- each setmaxnreg sits at the head of the branch it governs (one instruction per
+    // warpgroup, and ptxas allocates each branch against its own limit).
+    const bool epi_role = warp >= RW_EPI_WARP0 && warp < RW_EPI_WARP0 + RW_EPI;
+    if (!epi_role) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         // =============================== front warp ==============================================================
+        RPROF_DECL;
         int t_ahead = 0;
         if (lane == 0) t_ahead = atomicAdd(&p.ticket[0], 1);
         for (int k = 0;; ++k) {
             const int slot = k % RW_SLOTS;
             const int t = __shfl_sync(0xffffffffu, t_ahead, 0);
             if (lane == 0 && t < p.n_tmpl) t_ahead = atomicAdd(&p.ticket[0], 1);
+            RPROF_BEGIN;
             mbar_wait(&s_slot_empty[slot], ((uint32_t)(k / RW_SLOTS) & 1u) ^ 1u);
+            RPROF_END(0);
             if (t >= p.n_tmpl) {  // out of work: stop slot
                 if (lane == 0) {
                     slot_header(slot)->t = -1;
                     mbar_arrive(&s_slot_full[slot]);
                 }
+                RPROF_DONE(0);
                 break;
             }
             if (lane == 0) {  // the copy's completion is the slot's `full` signal
@@ -311,17 +349,24 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
         }
     } else if (warp == 1) {
         // =============================== MMA issue ===============================================================
+        RPROF_DECL;
         int stage = 0;
         uint32_t sphase = 0;
         const uint32_t st0 = smem_u32(stages), ms = smem_u32(master);
         const uint32_t lbo_a = (uint32_t)MG * 128u;
-        const uint64_t d_b_hi = umma_desc(st0, 32 * 128, 128), d_b_lo = umma_desc(st0 + RW_B_BYTES, 32 * 128, 128);
+        const uint64_t d_b_hi = umma_desc(st0, RW_LBO, RW_SBO), d_b_lo = umma_desc(st0 + RW_B_BYTES, RW_LBO, RW_SBO);
         const uint32_t idesc = umma_idesc(Wp);
+        const uint64_t d_a_hi0 = umma_desc(ms, lbo_a, 128), d_a_lo0 = umma_desc(ms + master_part, lbo_a, 128);
         for (int k = 0;; ++k) {
             const int slot = k % RW_SLOTS;
+            RPROF_BEGIN;
             mbar_wait(&s_slot_full[slot], (uint32_t)(k / RW_SLOTS) & 1u);
+            RPROF_END(0);
             const RowsHeader *hd = slot_header(slot);
-            if (hd->t < 0) break;
+            if (hd->t < 0) {
+                RPROF_DONE(1);
+                break;
+            }
             const unsigned mask = hd->mask;
             unsigned m[2] = {mask & range[0], mask & range[1]};
             if (elect_one()) {
@@ -338,19 +383,24 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
                 while (all) {
                     const int c = __ffs(all) - 1;
                     all &= all - 1;
+                    RPROF_BEGIN;
                     mbar_wait(&s_stage_full[stage], sphase);
+                    RPROF_END(1);
                     tc_fence_after();
                     const uint64_t so = (uint64_t)((uint32_t)stage * (RW_STAGE_BYTES >> 4));
                     for (int h = 0; h < n_halves; ++h) {
                         if (!((m[h] >> c) & 1u)) continue;
                         const bool first = (m[h] & ((1u << c) - 1u)) == 0u, last = (m[h] >> c) == 1u;
                         if (first) {  // the epilogue has drained template k - 1
+                            RPROF_BEGIN;
                             mbar_wait(&s_half_empty[h], ((uint32_t)k & 1u) ^ 1u);
+                            RPROF_END(2);
                             tc_fence_after();
                         }
-                        // window of the master: rows 128 h + RP - 16 c .. + 127
-                        const uint32_t a0 = ms + (uint32_t)((128 * h + geo.RP - 16 * c - geo.d_min) >> 3) * 128u;
-                        const uint64_t d_a_hi = umma_desc(a0, lbo_a, 128), d_a_lo = umma_desc(a0 + master_part, lbo_a, 128);
+                        // window of the master: rows 128 h + RP - 16 c .. + 127 = 8-row group 16 h - 2 c + (RP - d_min) / 8
+                        // (128 bytes each: 8 descriptor address units)
+                        const uint64_t wo = (uint64_t)(uint32_t)(8 * (16 * h - 2 * c + ((geo.RP - geo.d_min) >> 3)));
+                        const uint64_t d_a_hi = d_a_hi0 + wo, d_a_lo = d_a_lo0 + wo;
                         const uint32_t d = tm + (uint32_t)(h * 256);
                         umma(d, d_a_hi, d_b_hi + so, idesc, first ? 0u : 1u);
                         umma(d, d_a_hi, d_b_lo + so, idesc, 1);
@@ -368,7 +418,97 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
-    } else if (warp >= RW_EPI_WARP0 && warp < RW_EPI_WARP0 + RW_EPI) {
+    } else if ((warp < RW_EPI_WARP0 ? warp - 2 : warp - (RW_EPI_WARP0 + RW_EPI) + 2) < RW_PROD) {
+        // =============================== B producers ==============================================================
+        // All sixteen warps work on the same chunk, one row each (the time to fill a stage is one row's latency); lane =
+        // 8-pixel unit, so the row's reflections are a warp-uniform loop and a reflection costs two table loads and
+        // eight FMAs per lane.
+        const int pi = warp < RW_EPI_WARP0 ? warp - 2 : warp - (RW_EPI_WARP0 + RW_EPI) + 2;  // 0 .. RW_PROD - 1 = row of the chunk
+        LutRef L;
+        L.base = smem_u32(lut);
+        L.n4 = p.n4;
+        L.last = p.n4 - 1;
+        L.bias = R + LUT_PAD;
+        const int x_lo = 8 * lane;
+        const bool unit_ok = x_lo < Wp;
+        // row pi of the chunk: K group pi >> 3, 16 (pi & 7) inside the core matrix
+        const uint32_t b_row = smem_u32(stages) + (uint32_t)((pi >> 3) * RW_LBO + (pi & 7) * 16) + (uint32_t)lane * RW_SBO;
+        RPROF_DECL;
+        int c = 0;
+        for (int k = 0;; ++k) {
+            const int slot = k % RW_SLOTS;
+            RPROF_BEGIN;
+            mbar_wait(&s_slot_full[slot], (uint32_t)(k / RW_SLOTS) & 1u);
+            RPROF_END(0);
+            const RowsHeader *hd = slot_header(slot);
+            if (hd->t < 0) {
+                if (pi == 0) { RPROF_DONE(3); }
+                break;
+            }
+            const uint32_t spot_s = smem_u32(slots + (size_t)slot * slot_bytes + 32);
+            const uint32_t off_s = smem_u32(slots + (size_t)slot * slot_bytes + rows_offsets_offset(p.cap));
+            unsigned all = hd->mask & (range[0] | range[1]);
+            for (; all; all &= all - 1, ++c) {
+                const int ce = __ffs(all) - 1;
+                const int stage = c % RW_NP;
+                const uint32_t b_hi = b_row + (uint32_t)stage * RW_STAGE_BYTES, b_lo = b_hi + RW_B_BYTES;
+                // this warp's row and its reflections (read before the wait for the stage)
+                const int src = rows_source(16 * ce + pi, geo.RP, R, H);
+                int s0 = 0, s1 = 0;
+                if (src >= 0) {
+                    s0 = (int)lds16(off_s + 2u * (uint32_t)src);
+                    s1 = (int)lds16(off_s + 2u * (uint32_t)src + 2u);
+                }
+                float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+                // += am * taps a .. a + 7 of the padded kernel for this lane's unit, a = a0 + 8 lane: a0 is the same for every
+                // lane, so the table copy (a & 3) and the entry ((a >> 2) = (a0 >> 2) + 2 lane) split into a warp-uniform
+                // part and 32 lane; lanes outside [lane_lo, lane_hi] read the all-zero head of the table
+                auto add_taps = [&](int a0, int lane_lo, int lane_hi, float am) {
+                    const uint32_t ad = (lane >= lane_lo && lane <= lane_hi)
+                                            ? L.base + (uint32_t)((((a0 & 3) * L.n4 + (a0 >> 2)) << 4) + 32 * lane)
+                                            : L.base;
+                    const float4 u0 = lds128(ad), u1 = lds128(ad + 16u);
+                    w0 = make_float4(fmaf(am, u0.x, w0.x), fmaf(am, u0.y, w0.y), fmaf(am, u0.z, w0.z), fmaf(am, u0.w, w0.w));
+                    w1 = make_float4(fmaf(am, u1.x, w1.x), fmaf(am, u1.y, w1.y), fmaf(am, u1.z, w1.z), fmaf(am, u1.w, w1.w));
+                };
+                uint2 r_next = make_uint2(0u, 0u);
+                if (s0 < s1) r_next = lds64v(spot_s + 8u * (uint32_t)s0);  // (the same word for every lane)
+                for (int s = s0; s < s1; ++s) {
+                    const uint2 r = r_next;
+                    if (s + 1 < s1) r_next = lds64v(spot_s + 8u * (uint32_t)(s + 1));
+                    const int cx = (int)(r.x & 0xffffu);
+                    const float am = __uint_as_float(r.y);
+                    // direct image: offsets d = 8 lane - cx in [-R - 7, R]
+                    add_taps(L.bias - cx, (cx - R) >> 3, (cx + R) >> 3, am);
+                    if (cx < R)  // mirror image at -cx - 1 (warp-uniform): d2 = 8 lane + cx + 1 <= R
+                        add_taps(L.bias + cx + 1, 0, (R - cx - 1) >> 3, am);
+                    if (cx >= W - R)  // mirror image at 2 W - 1 - cx: d3 = 8 lane + cx + 1 - 2 W in [-R - 7, R]
+                        add_taps(L.bias + cx + 1 - 2 * W, (2 * W - cx - 1 - R) >> 3, (2 * W - cx - 1 + R) >> 3, am);
+                }
+                uint32_t h[4] = {0u, 0u, 0u, 0u}, l[4] = {0u, 0u, 0u, 0u};
+                if (s0 != s1) {  // (warp-uniform)
+                    bf16_split2(w0.x, w0.y, h[0], l[0]);
+                    bf16_split2(w0.z, w0.w, h[1], l[1]);
+                    bf16_split2(w1.x, w1.y, h[2], l[2]);
+                    bf16_split2(w1.z, w1.w, h[3], l[3]);
+                }
+                RPROF_BEGIN;
+                mbar_wait(&s_stage_empty[stage], ((uint32_t)(c / RW_NP) & 1u) ^ 1u);
+                RPROF_END(1);
+                if (unit_ok) {
+                    sts128(b_hi, h[0], h[1], h[2], h[3]);
+                    sts128(b_lo, l[0], l[1], l[2], l[3]);
+                }
+                proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_stage_full[stage]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
+        }
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // =============================== epilogue (as in render_umma.cu) ========================================
         const int ew = warp - RW_EPI_WARP0;  // 0..7
         const int q = warp & 3;              // tensor-memory lane quarter this warp may read
@@ -377,12 +517,18 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
         const int n_ct = (W + 31) >> 5;
         const uint32_t tm_q = tm + ((uint32_t)(32 * q) << 16);
         int nbuf = 0;  // staged tiles so far (buffer = nbuf & 1)
+        RPROF_DECL;
         for (int k = 0;; ++k) {
             const int slot = k % RW_SLOTS;
+            RPROF_BEGIN;
             mbar_wait(&s_slot_full[slot], (uint32_t)(k / RW_SLOTS) & 1u);
+            RPROF_END(0);
             const RowsHeader *hd = slot_header(slot);
             const int t = hd->t;
-            if (t < 0) break;
+            if (t < 0) {
+                if (ew == 0) { RPROF_DONE(2); }
+                break;
+            }
             const bool norm = p.normalize && hd->n_live > 0;  // no spot in frame: zeros, returned un-normalised
             float scale = 1.f, vmax = INFINITY, clamp = __uint_as_float(0x7fc00000u);
             if (norm) {
@@ -390,7 +536,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
                 float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll 1
                 for (int h = 0; h < n_halves; ++h) {
+                    RPROF_BEGIN;
                     mbar_wait(&s_half_full[h], (uint32_t)k & 1u);
+                    RPROF_END(1);
                     tc_fence_after();
                     if (128 * h + 32 * q >= H) continue;  // none of this warp's rows is in the image (warp-uniform)
                     const bool row_ok = 128 * h + 32 * q + lane < H;
@@ -419,7 +567,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
                 }
                 float m = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                 if (lane == 0) s_emax[k & 1][ew] = m;
+                RPROF_BEGIN;
                 asm volatile("bar.sync 1, %0;" ::"n"(RW_EPI * 32) : "memory");
+                RPROF_END(2);
 #pragma unroll
                 for (int e = 0; e < RW_EPI; ++e) m = fmaxf(m, s_emax[k & 1][e]);
                 vmax = m;
@@ -485,98 +635,6 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
             if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
         }
         if (elect_one()) tma_store_wait_read<0>();
-    } else {
-        // =============================== B producers ==============================================================
-        const int pi = warp < RW_EPI_WARP0 ? warp - 2 : warp - (RW_EPI_WARP0 + RW_EPI) + 2;  // 0..5
-        const int pw = pi >> 1, kg = pi & 1;  // team (= its stage), K group (rows 8 kg .. 8 kg + 7 of a chunk)
-        const int k8 = lane & 7, gq = lane >> 3;  // this lane: row k8 of the K group, units 8 gq .. 8 gq + 7
-        LutRef L;
-        L.base = smem_u32(lut);
-        L.n4 = p.n4;
-        L.last = p.n4 - 1;
-        L.bias = R + LUT_PAD;
-        const uint32_t b_hi = smem_u32(stages) + (uint32_t)pw * RW_STAGE_BYTES + (uint32_t)(kg * (32 * 128) + k8 * 16);
-        const uint32_t b_lo = b_hi + RW_B_BYTES;
-        const int n_units = Wp >> 3;
-        int c = 0;
-        for (int k = 0;; ++k) {
-            const int slot = k % RW_SLOTS;
-            mbar_wait(&s_slot_full[slot], (uint32_t)(k / RW_SLOTS) & 1u);
-            const RowsHeader *hd = slot_header(slot);
-            if (hd->t < 0) break;
-            const uint32_t spot_s = smem_u32(slots + (size_t)slot * slot_bytes + 32);
-            const uint32_t off_s = smem_u32(slots + (size_t)slot * slot_bytes + rows_offsets_offset(p.cap));
-            unsigned all = hd->mask & (range[0] | range[1]);
-            for (; all; all &= all - 1, ++c) {
-                if (c % RW_NP != pw) continue;
-                const int ce = __ffs(all) - 1;
-                // this lane's row and its reflections
-                const int src = rows_source(16 * ce + 8 * kg + k8, geo.RP, R, H);
-                int s0 = 0, s1 = 0;
-                if (src >= 0) {
-                    s0 = (int)lds16(off_s + 2u * (uint32_t)src);
-                    s1 = (int)lds16(off_s + 2u * (uint32_t)src + 2u);
-                }
-                mbar_wait(&s_stage_empty[pw], ((uint32_t)(c / RW_NP) & 1u) ^ 1u);
-                if (s0 == s1) {
-                    // no reflection in this lane's row: zeros (most rows of a sparse template)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int g = 8 * gq + i;
-                        if (g < n_units) {
-                            sts128(b_hi + 128u * (uint32_t)g, 0u, 0u, 0u, 0u);
-                            sts128(b_lo + 128u * (uint32_t)g, 0u, 0u, 0u, 0u);
-                        }
-                    }
-                } else {
-                    // the lane's eight units accumulate in registers over the row's reflections (every unit loop is fully
-                    // unrolled: independent chains for the scheduler, static register indices)
-                    float4 w0[8], w1[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) w0[i] = w1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int xq = 64 * gq;
-                    auto add_taps = [&](int i, int a, float am) {  // unit i += am * taps a .. a + 7 of the padded kernel
-                        const uint32_t ad = fetch_addr(L, a);
-                        const float4 u0 = lds128(ad), u1 = lds128(ad + 16u);
-                        w0[i] = make_float4(fmaf(am, u0.x, w0[i].x), fmaf(am, u0.y, w0[i].y), fmaf(am, u0.z, w0[i].z), fmaf(am, u0.w, w0[i].w));
-                        w1[i] = make_float4(fmaf(am, u1.x, w1[i].x), fmaf(am, u1.y, w1[i].y), fmaf(am, u1.z, w1[i].z), fmaf(am, u1.w, w1[i].w));
-                    };
-                    for (int s = s0; s < s1; ++s) {
-                        const uint2 r = lds64v(spot_s + 8u * (uint32_t)s);
-                        const int cx = (int)(r.x & 0xffffu);
-                        const float am = __uint_as_float(r.y);
-                        const int dx = xq - cx;  // offset of the lane's first pixel from the reflection
-                        if (dx + 63 >= -R && dx <= R) {  // direct image
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (dx + 8 * i + 7 >= -R && dx + 8 * i <= R) add_taps(i, dx + 8 * i + L.bias, am);
-                        }
-                        const int d2 = xq + cx + 1;  // mirror image at -cx - 1
-                        if (d2 <= R) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (d2 + 8 * i <= R) add_taps(i, d2 + 8 * i + L.bias, am);
-                        }
-                        const int d3 = d2 - 2 * W;  // mirror image at 2 W - 1 - cx (d3 + 8 i <= 0 for every pixel of the image)
-                        if (d3 + 63 >= -R) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (d3 + 8 * i + 7 >= -R) add_taps(i, d3 + 8 * i + L.bias, am);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int g = 8 * gq + i;
-                        if (g < n_units) store_split8(b_hi + 128u * (uint32_t)g, b_lo + 128u * (uint32_t)g, w0[i], w1[i], 1.0f);
-                    }
-                }
-                proxy_fence();  // the stores above become visible to the tensor core's (async proxy) reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_stage_full[pw]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_slot_empty[slot]);
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -594,25 +652,45 @@ int launch_render_rows(RenderParams p, unsigned char *records, cudaStream_t st) 
     const RowsGeom geo = rows_geom(p.radius, p.H);
     if (geo.n_chunks > 32) return 0;
     const int slot_bytes = rows_record_bytes(p.cap);
-    int epi_bufs = 2;
-    auto smem_for = [&](int bufs) {
-        return (size_t)RW_NP * RW_STAGE_BYTES + (size_t)RW_EPI * bufs * RW_TILE_BYTES + (size_t)4 * (geo.master_rows >> 3) * 128 +
+    int epi_bufs = 2, n_stages = RW_NP_MAX;
+    auto smem_for = [&](int bufs, int stages) {
+        return (size_t)stages * RW_STAGE_BYTES + (size_t)RW_EPI * bufs * RW_TILE_BYTES + (size_t)4 * (geo.master_rows >> 3) * 128 +
                lut_smem_bytes(p.n4) + (size_t)RW_SLOTS * slot_bytes;
     };
-    if (smem_for(2) > 226 * 1024) epi_bufs = 1;
-    const size_t smem = smem_for(epi_bufs);
+    // as many stages as fit next to two staged tiles per epilogue warp, at least three
+    while (n_stages > 3 && smem_for(2, n_stages) > 226 * 1024) --n_stages;
+    {
+        const int o = option(OPT_RENDER_ROWS_STAGES);
+        if (o >= 3 && o <= RW_NP_MAX && smem_for(2, o) <= 226 * 1024) n_stages = o;
+    }
+    if (smem_for(2, n_stages) > 226 * 1024) epi_bufs = 1;
+    const size_t smem = smem_for(epi_bufs, n_stages);
     if (smem > 226 * 1024) return 0;  // (+ ~1 KB of static shared memory: barriers, alignment)
     alignas(64) CUtensorMap tmap;
     const int rt = make_image_tensor_map(&tmap, p.images, p.n_tmpl, p.H, p.W, 32, 32, true);
     if (rt != 0) return rt < 0 ? rt : 0;
     const int rc0 = launch_render_prepare_rows(p, records, st);
     if (rc0 != 0) return rc0;
-    cudaFuncSetAttribute(render_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     const int sms = num_sms();
     const int grid = p.n_tmpl < sms ? p.n_tmpl : sms;
-    render_rows_kernel<<<grid, RW_THREADS, smem, st>>>(p, tmap, records, slot_bytes, epi_bufs);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        kern<<<grid, RW_THREADS, smem, st>>>(p, tmap, records, slot_bytes, epi_bufs);
+    };
+    switch (n_stages) {  // (a compile-time stage count: the stage arithmetic sits on every role's critical path)
+        case 3: launch(render_rows_kernel<3>); break;
+        case 4: launch(render_rows_kernel<4>); break;
+        case 5: launch(render_rows_kernel<5>); break;
+        default: launch(render_rows_kernel<6>); break;
+    }
     const int rc = check_launch("ds_render (tcgen05, rows)");
     return rc == 0 ? 1 : rc;
 }
 
 }  // namespace ds
+
+#ifdef DS_PROF
+extern "C" int ds_debug_rows_prof(unsigned long long *out_host /*[16]*/) {
+    return cudaMemcpyFromSymbol(out_host, ds::g_rw_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -19,7 +19,7 @@ def golden_dir():
 
 
 OPTION_NAMES = ("render_pipe", "render_group", "render_fronts", "render_pipe_maxcap", "render_nostage", "render_mma",
-                "render_mma_min", "render_mma_tmpl_min", "render_umma", "render_umma_window", "render_zero_tma", "render_umma_team", "render_rows", "sim_lines", "sim_split", "sim_cta", "sim_stash")
+                "render_mma_min", "render_mma_tmpl_min", "render_umma", "render_umma_window", "render_zero_tma", "render_umma_team", "render_rows", "render_rows_stages", "sim_lines", "sim_split", "sim_cta", "sim_stash")
 
 
 @pytest.fixture

@@ -36,14 +36,18 @@ for cap, shape in ((288, (256, 256)), (160, (100, 152)), (1024, (96, 200))):
     X[..., :2] = rng.uniform(-1.05, 1.05, (n, cap, 2)) * (shape[1] / 256, shape[0] / 256)
     I = rng.uniform(1, 500, (n, cap))
     cnt = torch.tensor([cap, cap // 2, 17], dtype=torch.int32, device=engine.device())
-    for umma, pipe in ((1, -1), (0, 1), (0, 0)):     # tcgen05 kernel (+ prepare pass), pipelined, phase-synchronous
+    # tcgen05 kernels (per-reflection product with 2- and 4-warp producer teams, row-binned banded product; + their
+    # prepare passes), pipelined, phase-synchronous
+    for umma, pipe, rows, team in ((1, -1, 0, 2), (1, -1, 0, 4), (1, -1, 1, -1), (0, 1, -1, -1), (0, 0, -1, -1)):
         _cabi.set_option("render_umma", umma)
         _cabi.set_option("render_pipe", pipe)
+        _cabi.set_option("render_rows", rows)
+        _cabi.set_option("render_umma_team", team)
         for normalize in (True, False):
             engine.render(cnt, torch.as_tensor(X, device=engine.device()), torch.as_tensor(I, device=engine.device()),
                           shape, 7.0, 1 / 128, ((shape[1] - 1) / 2, (shape[0] - 1) / 2), normalize=normalize)
-_cabi.set_option("render_umma", -1)
-_cabi.set_option("render_pipe", -1)
+for k in ("render_umma", "render_pipe", "render_rows", "render_umma_team"):
+    _cabi.set_option(k, -1)
 _cabi.set_option("sim_lines", 1)
 gt = gen._g_table(cases.phase("si"), 2.0, True, cases.DW)
 engine.simulate(gt, random_quats(40, 1), gen.wavelength, 0.01, 0.01, "lorentzian")
@@ -55,10 +59,17 @@ for lines in (0, 1):
     engine.simulate(plan.run(0.5e-20, compact=False), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 engine.simulate(plan.run(0.5e-20), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 _cabi.set_option("sim_lines", -1)
-# few rotations over a large table (2 warps per CTA), the factorised structure factors (>= 4096 rows, >= 32 atoms),
-# the SO(3) grids
+# few rotations over a large table (one CTA per rotation: default stash, a small pool, the fall-back; 2 warps per CTA),
+# the factorised structure factors (>= 4096 rows, >= 32 atoms: box kernel), the SO(3) grids
 plan = gen._g_plan(cases.phase("large"), 1.6, True, cases.DW)
-engine.simulate(plan.run(0.0), random_quats(40, 3), gen.wavelength, 0.01, 0.01, "lorentzian")
+gt_large = plan.run(0.0)
+for cta, stash in ((-1, -1), (1, 512), (1, 64), (0, -1)):
+    _cabi.set_option("sim_cta", cta)
+    _cabi.set_option("sim_stash", stash)
+    engine.simulate(gt_large, random_quats(40, 3), gen.wavelength, 0.01, 0.01, "lorentzian")
+    engine.simulate(gt_large, random_quats(9, 4), gen.wavelength, 0.01, 0.01, "sin2c", precession_rad=0.005)
+_cabi.set_option("sim_cta", -1)
+_cabi.set_option("sim_stash", -1)
 from diffsims_b200.generators.rotation_list_generators import fundamental_zone_device, local_grid_device
 fundamental_zone_device(12, point_group="m-3m")
 local_grid_device(10, center=(10, 20, 30), grid_width=30)
