@@ -627,6 +627,23 @@ def main():
         e2e["d2h_roof"] = dict(gbytes_per_s_all_ranks=roof, gbytes_per_s_this_rank=roof_rank,
                                how="every rank: cudaMemcpyAsync of a 1 GiB device buffer into two pinned 1 GiB host slots for 1 s, "
                                    "concurrently, no kernels", e2e_fraction_of_roof=e2e["gbytes_per_s"] / roof)
+        # ---- the optional 16-bit export of the same templates (rint(v * 65535); half the device->host bytes)
+        ring16 = [torch.empty((chunk, H, W), dtype=torch.uint16).pin_memory() for _ in range(4)]
+        builder.run_host(q_pin, ring=ring16, chunk=chunk)
+        barrier()
+        u0, u1 = _events()
+        n_u = 2
+        u0.record()
+        for _ in range(n_u):
+            h2d_u, d2h_u = builder.run_host(q_pin, ring=ring16, chunk=chunk)
+        u1.record()
+        barrier()
+        tu = max_over_ranks(u0.elapsed_time(u1))
+        e2e["e2e_uint16"] = dict(value=world * B * n_u / (tu * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d_u),
+                                 d2h_bytes_per_step=int(d2h_u), steps=n_u, gbytes_per_s=world * B * n_u / (tu * 1e-3) * H * W * 2 / 1e9,
+                                 api="TemplateLibraryBuilder.run_host into uint16 ring buffers: ds_render (float32) -> ds_quantize_u16 "
+                                     "-> host; optional export, quantisation 7.6e-6 of the peak; float32 stays the headline")
+        del ring16
         # ---- spot lists end to end: what calculate_diffraction2d returns (+ the polar arrays pyxem's matcher consumes)
         for _ in range(1):
             builder.run_host_spots(q_pin, polar=True)

@@ -15,7 +15,7 @@ _lib = None
 
 # every symbol include/diffsims_b200.h declares
 SYMBOLS = ("ds_abi_version", "ds_last_error", "ds_set_option", "ds_get_option", "ds_structure_factors_scratch_bytes", "ds_structure_factors", "ds_pack_gtable",
-           "ds_simulate", "ds_render_scratch_bytes", "ds_render_launch_count", "ds_render", "ds_pack_csr", "ds_polar_flatten", "ds_library_pixel_coords",
+           "ds_simulate", "ds_render_scratch_bytes", "ds_render_launch_count", "ds_render", "ds_pack_csr", "ds_quantize_u16", "ds_polar_flatten", "ds_library_pixel_coords",
            "ds_beam_grid_num_blocks", "ds_beam_grid", "ds_beam_points_num_blocks", "ds_beam_points", "ds_so3_grid_num_blocks", "ds_so3_grid")
 ABI_VERSION = 2
 
@@ -47,6 +47,7 @@ def lib():
     L.ds_simulate.argtypes = [P, I, P, I, P, P, P, D, D, D, D, I, D, D, D, I, P, P, P, P, P, P, I, P, P, P]
     L.ds_render.argtypes = [P, I, I, P, P, P, I, I, D, D, D, D, I, I, D, I, D, I, P, P, D]
     L.ds_pack_csr.argtypes = [P, I, I, P, P, P, P, P, P, P, P]
+    L.ds_quantize_u16.argtypes = [P, ctypes.c_int64, P, P]
     L.ds_polar_flatten.argtypes = [P, I, I, P, P, P, I, I, P, I, P, P, P, P]
     L.ds_library_pixel_coords.argtypes = [P, I, I, P, P, D, D, D, D, D, D, P]
     L.ds_beam_grid.argtypes = [P, I, I, P, I, P, D, P, P, P, P]

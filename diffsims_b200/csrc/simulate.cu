@@ -540,10 +540,10 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Few rotations over a large table: one CTA per rotation, the table split across the CTA's warps.
+// Large tables (>= 4096 rows): one CTA per rotation, the table split across the CTA's warps.
 //
 // With one warp per rotation a launch of a few hundred rotations over a 10^5-row table is bound by one warp's latency over
-// the whole table.  Here the eight warps of a CTA scan eight contiguous slices of the table (straight from L2 / L1: the
+// the whole table, and at any rotation count every CTA streams the table through shared memory tile by tile.  Here the eight warps of a CTA scan eight contiguous slices of the table (straight from L2 / L1: the
 // CTAs of an SM run in step and share the lines), so the rotation's reflections come out in table order as slice 0,
 // slice 1, ...:
 //   1. scan: float32 coarse test, candidate row indices into the stash (shared memory).  The stash is one pool of
@@ -597,28 +597,16 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
         int n_c = 0, n_have = 0;  // candidates so far (counted on even when the pool is exhausted); chunks held
         bool full = false;
         // (the rows of the next step are requested before this step's are tested: a slice streams from L2 at a few hundred
-        // nanoseconds per round trip, and a CTA per SM has only eight warps to hide it)
-        auto fetch = [&](int i0, float4 (&g)[4]) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + 32 * k + lane;
-                g[k] = i < row_hi ? __ldg(p.g_f32 + i) : make_float4(0.f, 0.f, 0.f, INFINITY);
-            }
-        };
-        float4 nxt[4];
-        fetch(row_lo, nxt);
-        for (int i0 = row_lo; i0 < row_hi; i0 += 128) {
-            float4 gk[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) gk[k] = nxt[k];
-            fetch(i0 + 128, nxt);
+        // nanoseconds per round trip, and a CTA per SM has only eight warps to hide it; slices are whole 128-row steps
+        // except at the end of the table, which takes the guarded step below)
+        auto test_block = [&](int i0, const float4 (&gk)[4]) {
             bool cands[4], any = false;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 cands[k] = coarse_test(fmaf(mz0, gk[k].x, fmaf(mz1, gk[k].y, mz2 * gk[k].z)), gk[k].w, cc);
                 any |= cands[k];
             }
-            if (!__any_sync(0xffffffffu, any)) continue;
+            if (!__any_sync(0xffffffffu, any)) return;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned mask = __ballot_sync(0xffffffffu, cands[k]);
@@ -640,6 +628,31 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
                 if (cands[k] && j < n_have * SIM_CHUNK) s_cand[at(j)] = i0 + 32 * k + lane;
                 n_c += n_new;
             }
+        };
+        const int full_end = row_lo + ((row_hi - row_lo) & ~127);
+        if (row_lo < full_end) {
+            float4 nxt[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nxt[k] = __ldg(p.g_f32 + row_lo + 32 * k + lane);
+            for (int i0 = row_lo; i0 < full_end; i0 += 128) {
+                float4 gk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) gk[k] = nxt[k];
+                if (i0 + 128 < full_end) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) nxt[k] = __ldg(p.g_f32 + i0 + 128 + 32 * k + lane);
+                }
+                test_block(i0, gk);
+            }
+        }
+        if (full_end < row_hi) {
+            float4 gk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = full_end + 32 * k + lane;
+                gk[k] = i < row_hi ? __ldg(p.g_f32 + i) : make_float4(0.f, 0.f, 0.f, INFINITY);
+            }
+            test_block(full_end, gk);
         }
         if (lane == 0) s_ncand[warp] = full ? -1 : n_c;
         __syncthreads();
@@ -874,14 +887,14 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // Measured on the 113 082-row table (tools/bench_k12_large.py): 512 rotations 351 / 308 / 488 us with 8 / 2 / 1 warps
     // per CTA, 2 048 rotations 428 / 993 / 1535 us.
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Few rotations over a large table: one CTA per rotation, the table split across its warps (simulate_cta_kernel).
-    // Measured on the 113 082-row table (tools/bench_k12_large.py), CTA per rotation vs warp per rotation: 128 rotations
-    // 98 vs 322 us, 512: 125 vs 333 us, 1 024: 182 vs 359 us, 2 048: 1 122 vs 405 us (the CTAs no longer run in step and
-    // every one streams the table from L2).  sim_cta = 0 never, 1 forces it; sim_stash = candidate capacity of a rotation
-    // (small values exercise the fall-back in the tests).
+    // Large tables: one CTA per rotation, the table split across its warps (simulate_cta_kernel).  Measured on the
+    // 113 082-row table (tools/bench_k12_large.py, profiles/r02_k12_large.txt), CTA per rotation vs warp per rotation:
+    // 128 rotations 123 vs 322 us, 512: 138 vs 329 us, 2 048: 337 vs 403 us, 16 384: 2 227 vs 2 434 us -- the CTAs of an SM
+    // walk the table in step and share its lines in L1, and nothing is staged through shared memory.  sim_cta = 0 never,
+    // 1 forces it; sim_stash = candidate capacity of a rotation (small values exercise the fall-back in the tests).
     {
         const int o = option(OPT_SIM_CTA);
-        if (!lines && n_g > 0 && (o > 0 || (o < 0 && n_g >= 4096 && n_rot <= 1024))) {
+        if (!lines && n_g > 0 && (o > 0 || (o < 0 && n_g >= 4096))) {
             int stash = option(OPT_SIM_STASH);
             if (stash < SIM_CHUNK) stash = 4096;
             int n_chunks = (stash + SIM_CHUNK - 1) / SIM_CHUNK;

@@ -376,6 +376,19 @@ def _render_scratch(dev, n, cap):
     return t
 
 
+def quantize_u16(images, out=None):
+    """Normalised float32 templates -> uint16 (rint(v * 65535)) on the device: the optional half-size export of a
+    template library (quantisation 1.5e-5 of the peak).  ``out``: a uint16 device tensor of the same shape."""
+    if images.dtype != torch.float32 or not images.is_contiguous():
+        raise ValueError("quantize_u16 needs a contiguous float32 device tensor")
+    if out is None:
+        out = torch.empty(images.shape, dtype=torch.uint16, device=images.device)
+    elif out.dtype != torch.uint16 or out.shape != images.shape or not out.is_contiguous():
+        raise ValueError("quantize_u16: `out` must be a contiguous uint16 tensor of the same shape")
+    _cabi.check(_cabi.lib().ds_quantize_u16(_stream(), images.numel(), _cabi.ptr(images), _cabi.ptr(out)), "ds_quantize_u16")
+    return out
+
+
 def render_launch_count(cap, shape, sigma, fast=True, mean_spots=None):
     """How many kernels ds_render launches for this configuration (1, or 2 when the tcgen05 path with its prepare
     pass is taken) -- the library's own dispatch rule, for honest launch accounting."""

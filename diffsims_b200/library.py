@@ -218,9 +218,15 @@ class TemplateLibraryBuilder:
         completed, ``consumer(lo, hi, host_view)`` is called (the slot is reused ``len(ring)`` chunks later, so the
         consumer must be done with the view when it returns).  The call synchronises at its end and RAISES
         ``CapacityError`` if any rotation produced more reflections than the rows hold (nothing is returned from a
-        truncated build).  Returns (h2d_bytes, d2h_bytes)."""
+        truncated build).  Returns (h2d_bytes, d2h_bytes).
+
+        Destinations of dtype ``torch.uint16`` receive the optional 16-bit export (``engine.quantize_u16``: normalised
+        templates as rint(v * 65535), half the device->host bytes); float32 is the default and the parity-tested form."""
         if (out_host is None) == (ring is None):
             raise ValueError("run_host needs exactly one of out_host= and ring=")
+        as_u16 = (ring[0] if ring is not None else out_host).dtype == torch.uint16
+        if as_u16 and not self.normalize:
+            raise ValueError("the uint16 export needs normalised templates (values in [0, 1])")
         dev = engine.device()
         n = quats_host.shape[0]
         H, W = self.shape
@@ -229,6 +235,7 @@ class TemplateLibraryBuilder:
             chunk = min(chunk, ring[0].shape[0])
         streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
         bufs = [torch.empty((min(chunk, n), H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+        bufs16 = [torch.empty((min(chunk, n), H, W), dtype=torch.uint16, device=dev) for _ in range(2)] if as_u16 else None
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
@@ -255,7 +262,11 @@ class TemplateLibraryBuilder:
                 self.render(spots, buf)
                 w = worst[(i & 1):(i & 1) + 1]
                 torch.maximum(w, spots.max_count, out=w)
-                dst.copy_(buf, non_blocking=True)
+                if as_u16:
+                    dst.copy_(engine.quantize_u16(buf, bufs16[i & 1][: hi - lo]), non_blocking=True)
+                    self.launches += 1
+                else:
+                    dst.copy_(buf, non_blocking=True)
                 if counts_host is not None:
                     counts_host[lo:hi].copy_(spots.count, non_blocking=True)
                     d2h += (hi - lo) * 4
@@ -264,7 +275,7 @@ class TemplateLibraryBuilder:
                     ev.record(st)
                     pending.append((ev, lo, hi, slot))
             h2d += (hi - lo) * 32
-            d2h += (hi - lo) * H * W * 4
+            d2h += (hi - lo) * H * W * (2 if as_u16 else 4)
         for st in streams:
             main.wait_stream(st)
         for ev, plo, phi, pslot in pending:

@@ -59,9 +59,14 @@ const char *ds_last_error(void);
  *       phase-synchronous / pipelined kernels and its thresholds
  *   render_umma (DS_RENDER_UMMA) 0/1: tcgen05 K3 kernel off / forced (default: by capacity and density hint)
  *   render_umma_window (DS_RENDER_UMMA_WINDOW) 0: tcgen05 K3 kernel without per-chunk column windows
- *   render_zero_tma (DS_RENDER_ZERO_TMA) 0: pipelined K3 kernel stores all-zero regions with st.global instead of TMA
+ *   render_umma_team (DS_RENDER_UMMA_TEAM) 4: tcgen05 per-reflection K3 kernel with four producer warps per stage
+ *   render_rows (DS_RENDER_ROWS) 0/1: row-binned tcgen05 K3 kernel off / forced (default: >= 320 reflections per template)
+ *   render_rows_stages (DS_RENDER_ROWS_STAGES) 3..6: operand stages of the row-binned kernel
+ *   render_zero_tma (DS_RENDER_ZERO_TMA) 1: pipelined K3 kernel stores all-zero regions through the TMA engine
  *   sim_lines (DS_SIM_LINES) 0/1: K2 scan-line cull off / forced
- *   sim_split (DS_SIM_SPLIT) 0/n: K2 g-table split across CTAs off / forced to n parts
+ *   sim_split (DS_SIM_SPLIT) 1/2/4/8: warps (= rotations) per CTA of the warp-per-rotation K2 kernel
+ *   sim_cta (DS_SIM_CTA) 0/1: CTA-per-rotation K2 kernel off / forced (default: tables of >= 4096 rows)
+ *   sim_stash (DS_SIM_STASH) n: candidate capacity of a rotation in the CTA-per-rotation K2 kernel (default 4096)
  * Thread safety of the library: entry points may be called concurrently from several host threads as long
  * as the calls use different streams and different output buffers (and different `ticket` words for
  * ds_render); one process may drive several devices.
@@ -219,6 +224,15 @@ int ds_pack_csr(void *stream, int32_t n_tmpl, int32_t cap, const int32_t *count 
                 const int64_t *offsets /*[n_tmpl + 1]*/, const int32_t *g_index /*[n_tmpl][cap]*/,
                 const double *xyz /*[n_tmpl][cap][3]*/, const double *intensity /*[n_tmpl][cap]*/,
                 int32_t *g_index_out /*[total]*/, double *xyz_out /*[total][3]*/, double *intensity_out /*[total]*/);
+
+/*
+ * Optional 16-bit export of NORMALISED templates (values in [0, 1], what Simulation2D.get_diffraction_pattern returns
+ * with the reference's default normalisation, diffsims/simulations/simulation2d.py:440-441):
+ * out[i] = rint(clamp(in[i], 0, 1) * 65535).  The quantisation step (1.5e-5 of the peak) is below the 1e-4 parity
+ * budget of the float32 templates; a host consumer that accepts uint16 halves the device->host bytes.  Both buffers
+ * 16-byte aligned.  float32 stays the product of ds_render; this is a separate, optional pass.
+ */
+int ds_quantize_u16(void *stream, int64_t n, const float *in /*[n]*/, uint16_t *out /*[n]*/);
 
 /*
  * Pixel coordinates of an old-api template library: rint((xy + offset) / calibration + half_shape) as int32

@@ -768,3 +768,31 @@ def test_objects_exposing_only_the_orix_and_diffpy_attribute_surface():
     np.testing.assert_array_equal(ref.get_diffraction_pattern(**kw), got.get_diffraction_pattern(**kw))
     one = gen.calculate_diffraction2d(MinPhase(phase), MinRotation(rot.data[:1]), reciprocal_radius=1.5)
     assert one.coordinates.size > 0
+
+
+def test_uint16_export_of_normalised_templates():
+    """The optional 16-bit export (ds_quantize_u16 / run_host into uint16 buffers): rint(v * 65535) of the float32
+    templates -- quantisation 0.5 / 65535 = 7.6e-6 of the peak, the maximum pixel stays exactly 65535."""
+    import torch
+    from diffsims_b200 import engine
+    from diffsims_b200.library import TemplateLibraryBuilder, active_quaternions
+    from tests.helpers import random_quats
+    gen = ds.SimulationGenerator(200)
+    b = TemplateLibraryBuilder(gen, make_phase(), reciprocal_radius=1.5, max_excitation_error=0.02, shape=(144, 200), sigma=4.0,
+                               calibration=1.5 / 72)
+    n = 37
+    q = torch.as_tensor(active_quaternions(random_quats(n, 4))).pin_memory()
+    f32 = torch.empty((n, 144, 200), dtype=torch.float32).pin_memory()
+    u16 = torch.empty((n, 144, 200), dtype=torch.uint16).pin_memory()
+    _, d2h_f = b.run_host(q, out_host=f32, chunk=16)
+    _, d2h_u = b.run_host(q, ring=[torch.empty((16, 144, 200), dtype=torch.uint16).pin_memory() for _ in range(2)], chunk=16,
+                          consumer=lambda lo, hi, view: u16[lo:hi].copy_(view))
+    assert d2h_u * 2 == d2h_f
+    ref = np.rint(np.clip(f32.numpy().astype(np.float64), 0, 1) * 65535)
+    got = u16.numpy().astype(np.float64)
+    assert np.abs(got - ref).max() <= 1          # (float32 product v * 65535 against the float64 one: ties only)
+    assert np.abs(got / 65535 - f32.numpy()).max() <= 0.5 / 65535 + 1e-7
+    assert all(got[i].max() == 65535 for i in range(n) if f32[i].max() > 0)
+    # odd sizes go through the scalar tail
+    x = torch.rand(1003, device=engine.device())
+    assert torch.equal(engine.quantize_u16(x).cpu().to(torch.int32), torch.round(x * 65535).cpu().to(torch.int32))

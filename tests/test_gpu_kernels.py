@@ -139,8 +139,11 @@ def test_simulate_reference_counts(eng):
     assert int(spots.count[0]) == 250
 
 
-def test_simulate_streaming_tiles_large_cell(eng):
-    """N_g > 6144 exercises the double-buffered cp.async.bulk tile path."""
+@pytest.mark.parametrize("cta", [0, 1])
+def test_simulate_streaming_tiles_large_cell(eng, opts, cta):
+    """N_g > 6144: the double-buffered cp.async.bulk tile path of the warp-per-rotation kernel (sim_cta = 0) and the
+    CTA-per-rotation kernel that large tables take by default, both against the oracle."""
+    opts(sim_cta=cta)
     phase = cases.phase("large")
     gs, gt = _gtable_new_api(eng, phase, 1.2, True, dw=cases.DW)
     assert gt.n > 6144
