@@ -247,11 +247,11 @@ structure_factor_tab_kernel(int n_g, const double *__restrict__ hkl, const doubl
 // the second (000) the new API appends, read the same entries).
 // ---------------------------------------------------------------------------------------------------
 constexpr int SFB_MAX_H = 63;
-// atom splits of the box kernel: enough CTAs to fill the GPU for cells of a few hundred atoms, result boxes <= 64 MB
+// result boxes (= atom units) of the box kernel: enough CTAs to fill the GPU for cells of a few hundred atoms, <= 64 MB
 inline int sfb_splits(int n_atoms, int H) {
     const long long W = 2ll * H + 1, box_bytes = W * W * W * 16;
-    long long s = (n_atoms + 63) / 64;
-    if (s > 8) s = 8;
+    long long s = (n_atoms + 31) / 32;
+    if (s > 16) s = 16;
     if (s * box_bytes > (64ll << 20)) s = (64ll << 20) / box_bytes;
     return s < 1 ? 1 : (int)s;
 }
@@ -271,140 +271,162 @@ __global__ void sf_box_scatter_kernel(int n_g, const double *__restrict__ hkl, i
     idx[((long long)h * W + k) * W + l] = g;  // (rows sharing an index triple: any of them, they share |g|)
 }
 
-template <int MODEL>
+// Units of the atom split: every unit is a run of at most `unit` atoms of ONE element (so that the element's scattering
+// factor can be applied after the sum), `unit` the smallest multiple of the tile size for which the units fit the result
+// boxes.  Returns the number of units; with u >= 0 also unit u's element and atom range.  (n_elem <= max_units.)
+__device__ __forceinline__ int sfb_units(const int *start, int n_elem, int max_units, int u, int &e_out, int &lo, int &hi) {
+    int unit = SFB_ATOMS, n_units;
+    for (;; unit += SFB_ATOMS) {
+        n_units = 0;
+        for (int e = 0; e < n_elem; ++e) n_units += (start[e + 1] - start[e] + unit - 1) / unit;
+        if (n_units <= max_units) break;
+    }
+    e_out = lo = hi = 0;
+    int at = 0;
+    for (int e = 0; e < n_elem && u >= 0; ++e) {
+        const int n_e = start[e + 1] - start[e], pieces = (n_e + unit - 1) / unit;
+        if (u < at + pieces) {
+            e_out = e;
+            lo = start[e] + (u - at) * unit;
+            hi = min(start[e + 1], lo + unit);
+            break;
+        }
+        at += pieces;
+    }
+    return n_units;
+}
+
 __global__ void __launch_bounds__(SFB_THREADS)
-structure_factor_box_kernel(const double *__restrict__ gnorm, int n_atoms, int n_elem, const int *__restrict__ elem_start,
-                            const double *__restrict__ coeffs, const double *__restrict__ dw, int H, int n_split, int n_ltiles,
-                            const double2 *__restrict__ table, const int *__restrict__ idx, double2 *__restrict__ Fbox) {
+structure_factor_box_kernel(int n_atoms, int n_elem, const int *__restrict__ elem_start, int H, int max_units, int n_ltiles,
+                            const double2 *__restrict__ table, const int *__restrict__ idx, double2 *__restrict__ Sbox) {
     extern __shared__ __align__(16) unsigned char sfb_smem[];
     double2 *s_P = reinterpret_cast<double2 *>(sfb_smem);        // [SFB_ATOMS][SFB_KT]: Ex_j[h] Ey_j[k]
     double2 *s_Z = s_P + SFB_ATOMS * SFB_KT;                     // [SFB_ATOMS][SFB_LT]: Ez_j[l]
-    __shared__ double s_coef[SF_MAX_ELEM * 10];
-    __shared__ double s_dw[SF_MAX_ELEM];
     __shared__ int s_start[SF_MAX_ELEM + 1];
     const int W = 2 * H + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wk = warp >> 1, wl = warp & 1, lk = lane >> 4, ll = lane & 15;
     const int h = blockIdx.y, k_cta = blockIdx.x * SFB_KT, l_cta = (blockIdx.z % n_ltiles) * SFB_LT;
-    // this CTA's share of the atoms (whole shared-memory tiles): the partial sums of the splits go to separate result
-    // boxes that the gather pass adds in a fixed order
-    const int split = blockIdx.z / n_ltiles;
-    const int tiles_per_split = ((n_atoms + SFB_ATOMS - 1) / SFB_ATOMS + n_split - 1) / n_split;
-    const int atom_lo = min(n_atoms, split * tiles_per_split * SFB_ATOMS);
-    const int atom_hi = min(n_atoms, atom_lo + tiles_per_split * SFB_ATOMS);
-    Fbox += (size_t)split * (size_t)(2 * H + 1) * (2 * H + 1) * (2 * H + 1);
+    const int unit = blockIdx.z / n_ltiles;
     // this thread's entries: k = k_cta + kq + rk (rk = 0..3), l = l_cta + lq + 16 rl (rl = 0, 1)
     const int kq = wk * 8 + lk * 4, lq = wl * 32 + ll;
-    int row[4][2];
-    bool any = false;
+    bool live[4][2], any = false;
 #pragma unroll
     for (int rk = 0; rk < 4; ++rk)
 #pragma unroll
         for (int rl = 0; rl < 2; ++rl) {
             const int k = k_cta + kq + rk, l = l_cta + lq + 16 * rl;
-            row[rk][rl] = (k < W && l < W) ? __ldg(idx + ((long long)h * W + k) * W + l) : -1;
-            any |= row[rk][rl] >= 0;
+            live[rk][rl] = (k < W && l < W) && __ldg(idx + ((long long)h * W + k) * W + l) >= 0;
+            any |= live[rk][rl];
         }
     const bool warp_live = __any_sync(0xffffffffu, any);
     if (!__syncthreads_or(warp_live)) return;  // no table row in this CTA's part of the box
-    for (int i = tid; i < n_elem * 10; i += SFB_THREADS) s_coef[i] = coeffs[i];
-    for (int i = tid; i < n_elem; i += SFB_THREADS) s_dw[i] = dw[i];
     for (int i = tid; i <= n_elem; i += SFB_THREADS) s_start[i] = elem_start[i];
-    double g2[4][2], Fre[4][2], Fim[4][2];
-#pragma unroll
-    for (int rk = 0; rk < 4; ++rk)
-#pragma unroll
-        for (int rl = 0; rl < 2; ++rl) {
-            const double gn = row[rk][rl] >= 0 ? __ldg(gnorm + row[rk][rl]) : 0.0;
-            g2[rk][rl] = gn * gn;
-            Fre[rk][rl] = Fim[rk][rl] = 0.0;
-        }
     __syncthreads();
+    int e_unit, atom_lo, atom_hi;
+    if (unit >= sfb_units(s_start, n_elem, max_units, unit, e_unit, atom_lo, atom_hi)) return;  // (uniform) unused unit
     const double2 *tab_x = table, *tab_y = table + (size_t)n_atoms * W, *tab_z = table + 2 * (size_t)n_atoms * W;
-
-    for (int e = 0; e < n_elem; ++e) {
-        const int e_lo = max(s_start[e], atom_lo), e_hi = min(s_start[e + 1], atom_hi);
-        if (e_lo >= e_hi) continue;  // (uniform) none of this element's atoms in this split
-        double re[4][2], im[4][2];
+    double re[4][2], im[4][2];
 #pragma unroll
-        for (int rk = 0; rk < 4; ++rk)
+    for (int rk = 0; rk < 4; ++rk)
 #pragma unroll
-            for (int rl = 0; rl < 2; ++rl) re[rk][rl] = im[rk][rl] = 0.0;
-        for (int base = e_lo; base < e_hi; base += SFB_ATOMS) {
-            const int n_tile = min(SFB_ATOMS, e_hi - base);
-            __syncthreads();  // the previous tile has been consumed
-            for (int i = tid; i < n_tile * SFB_KT; i += SFB_THREADS) {
-                const int j = i / SFB_KT, k = k_cta + i % SFB_KT;
-                double2 v = make_double2(0.0, 0.0);
-                if (k < W) {
-                    const double2 ex = __ldg(tab_x + (size_t)(base + j) * W + h), ey = __ldg(tab_y + (size_t)(base + j) * W + k);
-                    v = make_double2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
-                }
-                s_P[i] = v;
+        for (int rl = 0; rl < 2; ++rl) re[rk][rl] = im[rk][rl] = 0.0;
+    for (int base = atom_lo; base < atom_hi; base += SFB_ATOMS) {
+        const int n_tile = min(SFB_ATOMS, atom_hi - base);
+        __syncthreads();  // the previous tile has been consumed
+        for (int i = tid; i < n_tile * SFB_KT; i += SFB_THREADS) {
+            const int j = i / SFB_KT, k = k_cta + i % SFB_KT;
+            double2 v = make_double2(0.0, 0.0);
+            if (k < W) {
+                const double2 ex = __ldg(tab_x + (size_t)(base + j) * W + h), ey = __ldg(tab_y + (size_t)(base + j) * W + k);
+                v = make_double2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
             }
-            for (int i = tid; i < n_tile * SFB_LT; i += SFB_THREADS) {
-                const int j = i / SFB_LT, l = l_cta + i % SFB_LT;
-                s_Z[i] = l < W ? __ldg(tab_z + (size_t)(base + j) * W + l) : make_double2(0.0, 0.0);
-            }
-            __syncthreads();
-            if (!warp_live) continue;  // (warp-uniform; the barriers above are still taken)
-            for (int j = 0; j < n_tile; ++j) {
-                const double2 *pr = s_P + j * SFB_KT + kq, *zr = s_Z + j * SFB_LT + lq;
-                const double2 z0 = zr[0], z1 = zr[16];
+            s_P[i] = v;
+        }
+        for (int i = tid; i < n_tile * SFB_LT; i += SFB_THREADS) {
+            const int j = i / SFB_LT, l = l_cta + i % SFB_LT;
+            s_Z[i] = l < W ? __ldg(tab_z + (size_t)(base + j) * W + l) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        if (!warp_live) continue;  // (warp-uniform; the barriers above are still taken)
+        for (int j = 0; j < n_tile; ++j) {
+            const double2 *pr = s_P + j * SFB_KT + kq, *zr = s_Z + j * SFB_LT + lq;
+            const double2 z0 = zr[0], z1 = zr[16];
 #pragma unroll
-                for (int rk = 0; rk < 4; ++rk) {
-                    const double2 a = pr[rk];
-                    re[rk][0] = fma(a.x, z0.x, re[rk][0]);
-                    re[rk][0] = fma(-a.y, z0.y, re[rk][0]);
-                    im[rk][0] = fma(a.x, z0.y, im[rk][0]);
-                    im[rk][0] = fma(a.y, z0.x, im[rk][0]);
-                    re[rk][1] = fma(a.x, z1.x, re[rk][1]);
-                    re[rk][1] = fma(-a.y, z1.y, re[rk][1]);
-                    im[rk][1] = fma(a.x, z1.y, im[rk][1]);
-                    im[rk][1] = fma(a.y, z1.x, im[rk][1]);
-                }
+            for (int rk = 0; rk < 4; ++rk) {
+                const double2 a = pr[rk];
+                re[rk][0] = fma(a.x, z0.x, re[rk][0]);
+                re[rk][0] = fma(-a.y, z0.y, re[rk][0]);
+                im[rk][0] = fma(a.x, z0.y, im[rk][0]);
+                im[rk][0] = fma(a.y, z0.x, im[rk][0]);
+                re[rk][1] = fma(a.x, z1.x, re[rk][1]);
+                re[rk][1] = fma(-a.y, z1.y, re[rk][1]);
+                im[rk][1] = fma(a.x, z1.y, im[rk][1]);
+                im[rk][1] = fma(a.y, z1.x, im[rk][1]);
             }
         }
-#pragma unroll
-        for (int rk = 0; rk < 4; ++rk)
-#pragma unroll
-            for (int rl = 0; rl < 2; ++rl) {
-                if (row[rk][rl] < 0) continue;
-                // f_e(g^2) * exp(-g^2 B_e / 4): the real part of the reference's complex exponent (sim_utils.py:297-301)
-                const double fe = scattering_factor<MODEL>(g2[rk][rl], &s_coef[e * 10]) * exp(-0.25 * g2[rk][rl] * s_dw[e]);
-                Fre[rk][rl] = fma(fe, re[rk][rl], Fre[rk][rl]);
-                Fim[rk][rl] = fma(fe, im[rk][rl], Fim[rk][rl]);
-            }
     }
+    double2 *out = Sbox + (size_t)unit * W * W * W;
 #pragma unroll
     for (int rk = 0; rk < 4; ++rk)
 #pragma unroll
         for (int rl = 0; rl < 2; ++rl) {
-            if (row[rk][rl] < 0) continue;
+            if (!live[rk][rl]) continue;
             const int k = k_cta + kq + rk, l = l_cta + lq + 16 * rl;
-            Fbox[((long long)h * W + k) * W + l] = make_double2(Fre[rk][rl], Fim[rk][rl]);
+            out[((long long)h * W + k) * W + l] = make_double2(re[rk][rl], im[rk][rl]);
         }
 }
 
-__global__ void sf_box_gather_kernel(int n_g, const double *__restrict__ hkl, int H, int n_split, const double2 *__restrict__ Fbox,
-                                     const double *__restrict__ prefactor, double *__restrict__ F_out, double *__restrict__ I_out) {
+// F(row) = sum over the units, in order, of f_e(g^2) exp(-g^2 B_e / 4) S_unit[row's box entry]; the scattering factor of an
+// element is evaluated once per row
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+sf_box_gather_kernel(int n_g, const double *__restrict__ hkl, const double *__restrict__ gnorm, int H, int n_elem,
+                     const int *__restrict__ elem_start, const double *__restrict__ coeffs, const double *__restrict__ dw,
+                     int max_units, const double2 *__restrict__ Sbox, const double *__restrict__ prefactor,
+                     double *__restrict__ F_out, double *__restrict__ I_out) {
+    __shared__ double s_coef[SF_MAX_ELEM * 10];
+    __shared__ double s_dw[SF_MAX_ELEM];
+    __shared__ int s_start[SF_MAX_ELEM + 1];
+    __shared__ int s_unit_elem[32];
+    __shared__ int s_n_units;
+    for (int i = threadIdx.x; i < n_elem * 10; i += blockDim.x) s_coef[i] = coeffs[i];
+    for (int i = threadIdx.x; i < n_elem; i += blockDim.x) s_dw[i] = dw[i];
+    for (int i = threadIdx.x; i <= n_elem; i += blockDim.x) s_start[i] = elem_start[i];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int e, lo, hi;
+        const int n_units = sfb_units(s_start, n_elem, max_units, threadIdx.x, e, lo, hi);
+        s_unit_elem[threadIdx.x] = e;
+        if (threadIdx.x == 0) s_n_units = n_units;
+    }
+    __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_g) return;
     const int W = 2 * H + 1;
     const int h = (int)hkl[3 * g] + H, k = (int)hkl[3 * g + 1] + H, l = (int)hkl[3 * g + 2] + H;
-    double2 F = make_double2(0.0, 0.0);
-    for (int s = 0; s < n_split; ++s) {  // fixed order: reproducible sums
-        const double2 part = Fbox[(size_t)s * W * W * W + ((long long)h * W + k) * W + l];
-        F.x += part.x;
-        F.y += part.y;
+    const size_t entry = ((size_t)h * W + k) * W + l, box = (size_t)W * W * W;
+    const double g2 = gnorm[g] * gnorm[g];
+    double Fre = 0.0, Fim = 0.0, fe = 0.0;
+    int e_cur = -1;
+    for (int u = 0; u < s_n_units; ++u) {  // fixed order: reproducible sums (units are ordered by element)
+        const int e = s_unit_elem[u];
+        if (e != e_cur) {
+            // f_e(g^2) * exp(-g^2 B_e / 4): the real part of the reference's complex exponent (sim_utils.py:297-301)
+            fe = scattering_factor<MODEL>(g2, &s_coef[e * 10]) * exp(-0.25 * g2 * s_dw[e]);
+            e_cur = e;
+        }
+        const double2 part = Sbox[(size_t)u * box + entry];
+        Fre = fma(fe, part.x, Fre);
+        Fim = fma(fe, part.y, Fim);
     }
     if (F_out) {
-        F_out[2 * g] = F.x;
-        F_out[2 * g + 1] = F.y;
+        F_out[2 * g] = Fre;
+        F_out[2 * g + 1] = Fim;
     }
     if (I_out) {
         const double p = prefactor ? prefactor[g] : 1.0;
-        I_out[g] = p * (F.x * F.x + F.y * F.y);  // sim_utils.py:353
+        I_out[g] = p * (Fre * Fre + Fim * Fim);  // sim_utils.py:353
     }
 }
 
@@ -442,29 +464,29 @@ extern "C" int ds_structure_factors(void *stream, int32_t n_g, const double *hkl
         sf_phase_table_kernel<<<(unsigned)((n_tab + 255) / 256), 256, 0, st>>>(n_atoms, H, frac, occ, table);
         // tables that fill a good part of their index box: the register-tiled box kernel
         const long long box = (long long)W * W * W;
-        if (H <= SFB_MAX_H && box <= 16ll * n_g) {
+        const int max_units = sfb_splits(n_atoms, H);
+        if (H <= SFB_MAX_H && box <= 16ll * n_g && n_elem <= max_units) {
             unsigned char *after = static_cast<unsigned char *>(table_scratch) + n_tab * 16;
             int *idx = reinterpret_cast<int *>(after);
-            double2 *Fbox = reinterpret_cast<double2 *>(after + ((box * 4 + 15) & ~15ll));
+            double2 *Sbox = reinterpret_cast<double2 *>(after + ((box * 4 + 15) & ~15ll));
             sf_box_clear_kernel<<<(unsigned)((box + 255) / 256), 256, 0, st>>>(box, idx);
             sf_box_scatter_kernel<<<(n_g + 255) / 256, 256, 0, st>>>(n_g, hkl, H, idx);
-            const int n_split = sfb_splits(n_atoms, H), n_ltiles = (W + SFB_LT - 1) / SFB_LT;
-            const dim3 grid_b((W + SFB_KT - 1) / SFB_KT, W, n_ltiles * n_split);
+            const int n_ltiles = (W + SFB_LT - 1) / SFB_LT;
+            const dim3 grid_b((W + SFB_KT - 1) / SFB_KT, W, n_ltiles * max_units);
             const size_t smem_b = (size_t)SFB_ATOMS * (SFB_KT + SFB_LT) * 16;
-#define DS_SFB_LAUNCH(M)                                                                                                     \
-    do {                                                                                                                     \
-        cudaFuncSetAttribute(structure_factor_box_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);        \
-        structure_factor_box_kernel<M><<<grid_b, SFB_THREADS, smem_b, st>>>(gnorm, n_atoms, n_elem, elem_start, coeffs, dw, H, \
-                                                                            n_split, n_ltiles, table, idx, Fbox);            \
-    } while (0)
+            cudaFuncSetAttribute(structure_factor_box_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            structure_factor_box_kernel<<<grid_b, SFB_THREADS, smem_b, st>>>(n_atoms, n_elem, elem_start, H, max_units, n_ltiles, table,
+                                                                             idx, Sbox);
+#define DS_SFG_LAUNCH(M)                                                                                                      \
+    sf_box_gather_kernel<M><<<(n_g + 127) / 128, 128, 0, st>>>(n_g, hkl, gnorm, H, n_elem, elem_start, coeffs, dw, max_units, \
+                                                                Sbox, prefactor, F_out, I_out)
             if (scattering_model == DS_SCATT_LOBATO)
-                DS_SFB_LAUNCH(DS_SCATT_LOBATO);
+                DS_SFG_LAUNCH(DS_SCATT_LOBATO);
             else if (scattering_model == DS_SCATT_XTABLES)
-                DS_SFB_LAUNCH(DS_SCATT_XTABLES);
+                DS_SFG_LAUNCH(DS_SCATT_XTABLES);
             else
-                DS_SFB_LAUNCH(DS_SCATT_NONE);
-#undef DS_SFB_LAUNCH
-            sf_box_gather_kernel<<<(n_g + 255) / 256, 256, 0, st>>>(n_g, hkl, H, n_split, Fbox, prefactor, F_out, I_out);
+                DS_SFG_LAUNCH(DS_SCATT_NONE);
+#undef DS_SFG_LAUNCH
             return check_launch("ds_structure_factors (box)");
         }
         const int grid_t = (n_g + SFT_G_TILE - 1) / SFT_G_TILE;

@@ -47,8 +47,8 @@ def test_abi_argument_validation_without_gpu():
     # kernel) and 32 + 8 cap + 528 (row-binned kernel: row offsets), 16-aligned
     assert lib.ds_render_scratch_bytes(1000, 32) == 16 + 1000 * 816
     assert lib.ds_render_scratch_bytes(1000, 992) == 16 + 1000 * 12432
-    # phase tables | index box (int32, 16-aligned) | one result box (complex128) per atom split (8 for 500 atoms)
-    assert lib.ds_structure_factors_scratch_bytes(500, 30) == 3 * 500 * 61 * 16 + (61 ** 3 * 4 + 15) // 16 * 16 + 8 * 61 ** 3 * 16
+    # phase tables | index box (int32, 16-aligned) | one result box (complex128) per atom unit (up to 16)
+    assert lib.ds_structure_factors_scratch_bytes(500, 30) == 3 * 500 * 61 * 16 + (61 ** 3 * 4 + 15) // 16 * 16 + 16 * 61 ** 3 * 16
     assert lib.ds_structure_factors_scratch_bytes(40, 100) == 3 * 40 * 201 * 16      # H > 63: phase tables only
     assert lib.ds_render_launch_count(32, 256, 256, 40, 1, 3.8) == 1 and lib.ds_render_launch_count(288, 256, 256, 40, 1, 177.0) == 2
     assert lib.ds_render_launch_count(288, 512, 512, 40, 1, 177.0) == 1    # larger than a tensor-memory template: float32 kernels
