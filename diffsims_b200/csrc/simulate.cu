@@ -890,11 +890,15 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // Large tables: one CTA per rotation, the table split across its warps (simulate_cta_kernel).  Measured on the
     // 113 082-row table (tools/bench_k12_large.py, profiles/r02_k12_large.txt), CTA per rotation vs warp per rotation:
     // 128 rotations 123 vs 322 us, 512: 138 vs 329 us, 2 048: 337 vs 403 us, 16 384: 2 227 vs 2 434 us -- the CTAs of an SM
-    // walk the table in step and share its lines in L1, and nothing is staged through shared memory.  sim_cta = 0 never,
-    // 1 forces it; sim_stash = candidate capacity of a rotation (small values exercise the fall-back in the tests).
+    // walk the table in step and share its lines in L1, and nothing is staged through shared memory.  (24 406 rows: equal at
+    // 16 384 rotations, 81 vs 131 us at 512.)  sim_cta = 0 never, 1 forces it; sim_stash = candidate capacity of a rotation (small values exercise the fall-back in the tests).
     {
         const int o = option(OPT_SIM_CTA);
-        if (!lines && n_g > 0 && (o > 0 || (o < 0 && n_g >= 4096))) {
+        // default: tables too large to stay resident in the warp kernel's shared memory take it when they are very large
+        // or the rotations few; resident tables (<= 6144 rows) only when a launch cannot fill the warp kernel's CTAs
+        // (Fe3C at r = 2, 5 222 rows, 16 384 rotations: 160 us warp per rotation vs 271 us CTA per rotation)
+        const bool cta_auto = n_g >= 4096 && (n_g > SIM_RESIDENT_MAX_G ? (n_g >= 32768 || n_rot <= 2048) : n_rot < 1024);
+        if (!lines && n_g > 0 && (o > 0 || (o < 0 && cta_auto))) {
             int stash = option(OPT_SIM_STASH);
             if (stash < SIM_CHUNK) stash = 4096;
             int n_chunks = (stash + SIM_CHUNK - 1) / SIM_CHUNK;

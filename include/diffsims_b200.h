@@ -65,7 +65,7 @@ const char *ds_last_error(void);
  *   render_zero_tma (DS_RENDER_ZERO_TMA) 1: pipelined K3 kernel stores all-zero regions through the TMA engine
  *   sim_lines (DS_SIM_LINES) 0/1: K2 scan-line cull off / forced
  *   sim_split (DS_SIM_SPLIT) 1/2/4/8: warps (= rotations) per CTA of the warp-per-rotation K2 kernel
- *   sim_cta (DS_SIM_CTA) 0/1: CTA-per-rotation K2 kernel off / forced (default: tables of >= 4096 rows)
+ *   sim_cta (DS_SIM_CTA) 0/1: CTA-per-rotation K2 kernel off / forced (default: large tables, or few rotations over >= 4096 rows)
  *   sim_stash (DS_SIM_STASH) n: candidate capacity of a rotation in the CTA-per-rotation K2 kernel (default 4096)
  * Thread safety of the library: entry points may be called concurrently from several host threads as long
  * as the calls use different streams and different output buffers (and different `ticket` words for
