@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(SIM_THREADS, MODEL < 0 ? 2 : 3) simulate_kerne
 constexpr int SIM_CHUNK = 64;        // stash entries per chunk
 constexpr int SIM_MAX_CHUNKS = 255;  // chunk ids are bytes
 
-template <int MODEL>
+template <int MODEL, bool LINES>
 __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimParams p, const int n_chunks) {
     constexpr bool GENERAL = MODEL < 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -599,6 +599,94 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
         // (the rows of the next step are requested before this step's are tested: a slice streams from L2 at a few hundred
         // nanoseconds per round trip, and a CTA per SM has only eight warps to hide it; slices are whole 128-row steps
         // except at the end of the table, which takes the guarded step below)
+        // candidates of one ballot, in lane order, to the end of this warp's stash (one more chunk from the pool when needed)
+        auto append = [&](bool cand, int index) {
+            const unsigned mask = __ballot_sync(0xffffffffu, cand);
+            if (mask == 0u) return;
+            const int n_new = __popc(mask);
+            if (!full && n_c + n_new > n_have * SIM_CHUNK) {  // (at most one more chunk: 32 <= SIM_CHUNK)
+                int id = 0;
+                if (lane == 0) id = atomicAdd(&s_next, 1);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if (id < n_chunks) {
+                    if (lane == 0) my_ids[n_have] = (unsigned char)id;
+                    ++n_have;
+                    __syncwarp();
+                } else {
+                    full = true;
+                }
+            }
+            const int j = n_c + __popc(mask & ((1u << lane) - 1u));
+            if (cand && j < n_have * SIM_CHUNK) s_cand[at(j)] = index;
+            n_c += n_new;
+        };
+        if (LINES) {
+            // ---- scan-line cull (tables made of lattice lines g0 + i step): a line crosses the slab z_lo <= z' <= z_hi in
+            // one index interval, found in closed form; only those rows see the float32 test.  Each warp takes a contiguous
+            // run of lines, 32 at a time; the intervals of a batch are expanded into (line, i) items in table order and
+            // dealt to the lanes 32 items at a time (a line nearly parallel to the slab contributes many, most a few).
+            const int lines_per_warp = ((p.n_lines + SIM_WARPS * 32 - 1) / (SIM_WARPS * 32)) * 32;
+            const int L_lo = min(p.n_lines, warp * lines_per_warp), L_hi = min(p.n_lines, L_lo + lines_per_warp);
+            const float bz = fmaf(mz0, p.step[0], fmaf(mz1, p.step[1], mz2 * p.step[2]));  // dz' per index
+            const bool parallel = fabsf(bz) < 1e-3f;
+            const float inv_b = parallel ? 0.0f : 1.0f / bz;
+            for (int L0 = L_lo; L0 < L_hi; L0 += 32) {
+                const int Ln = L0 + lane;
+                int first = 0, cnt = 0, ilo = 0;
+                float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (Ln < L_hi) {
+                    g0 = __ldg(p.line_g0 + Ln);
+                    const int start = __ldg(p.line_start + Ln), len = __ldg(p.line_start + Ln + 1) - start;
+                    const float a = fmaf(mz0, g0.x, fmaf(mz1, g0.y, mz2 * g0.z));
+                    int ihi;
+                    if (!parallel) {
+                        float t0 = (p.z_lo - a) * inv_b, t1 = (p.z_hi - a) * inv_b;
+                        if (t0 > t1) {
+                            const float tmp = t0;
+                            t0 = t1;
+                            t1 = tmp;
+                        }
+                        ilo = max(0, (int)ceilf(t0 - 4e-3f));
+                        ihi = min(len - 1, (int)floorf(t1 + 4e-3f));
+                    } else {  // the line runs (almost) parallel to the slab: all of it or nothing
+                        const float slack = (float)len * fabsf(bz);
+                        ilo = 0;
+                        ihi = (a >= p.z_lo - slack && a <= p.z_hi + slack) ? len - 1 : -1;
+                    }
+                    cnt = max(0, ihi - ilo + 1);
+                    first = start + ilo;
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - cnt;
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    // the line of item t: the first lane whose inclusive count exceeds t
+                    int src = 0;
+#pragma unroll
+                    for (int stp = 16; stp > 0; stp >>= 1)
+                        if (__shfl_sync(0xffffffffu, incl, src + stp - 1) <= t) src += stp;
+                    src = min(src, 31);
+                    const int r = t - __shfl_sync(0xffffffffu, excl, src);
+                    const int index = __shfl_sync(0xffffffffu, first, src) + r;
+                    const float fi = (float)(__shfl_sync(0xffffffffu, ilo, src) + r);
+                    const float hx = __shfl_sync(0xffffffffu, g0.x, src), hy = __shfl_sync(0xffffffffu, g0.y, src),
+                                hz = __shfl_sync(0xffffffffu, g0.z, src);
+                    bool cand = false;
+                    if (t < total) {
+                        const float gx = fmaf(fi, p.step[0], hx), gy = fmaf(fi, p.step[1], hy), gz = fmaf(fi, p.step[2], hz);
+                        const float z = fmaf(mz0, gx, fmaf(mz1, gy, mz2 * gz));
+                        cand = coarse_test(z, fmaf(gx, gx, fmaf(gy, gy, gz * gz)), cc) && live_row(p, index);
+                    }
+                    append(cand, index);
+                }
+            }
+        } else {
         auto test_block = [&](int i0, const float4 (&gk)[4]) {
             bool cands[4], any = false;
 #pragma unroll
@@ -608,26 +696,7 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
             }
             if (!__any_sync(0xffffffffu, any)) return;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned mask = __ballot_sync(0xffffffffu, cands[k]);
-                if (mask == 0u) continue;
-                const int n_new = __popc(mask);
-                if (!full && n_c + n_new > n_have * SIM_CHUNK) {  // (at most one more chunk: 32 <= SIM_CHUNK)
-                    int id = 0;
-                    if (lane == 0) id = atomicAdd(&s_next, 1);
-                    id = __shfl_sync(0xffffffffu, id, 0);
-                    if (id < n_chunks) {
-                        if (lane == 0) my_ids[n_have] = (unsigned char)id;
-                        ++n_have;
-                        __syncwarp();
-                    } else {
-                        full = true;
-                    }
-                }
-                const int j = n_c + __popc(mask & ((1u << lane) - 1u));
-                if (cands[k] && j < n_have * SIM_CHUNK) s_cand[at(j)] = i0 + 32 * k + lane;
-                n_c += n_new;
-            }
+            for (int k = 0; k < 4; ++k) append(cands[k], i0 + 32 * k + lane);
         };
         const int full_end = row_lo + ((row_hi - row_lo) & ~127);
         if (row_lo < full_end) {
@@ -653,6 +722,7 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
                 gk[k] = i < row_hi ? __ldg(p.g_f32 + i) : make_float4(0.f, 0.f, 0.f, INFINITY);
             }
             test_block(full_end, gk);
+        }
         }
         if (lane == 0) s_ncand[warp] = full ? -1 : n_c;
         __syncthreads();
@@ -831,12 +901,20 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // <~ 3e-7 |g|; 8e-6 max(1, |g|max) leaves > 20x head-room and admits < 0.1 % extra candidates.
     p.coarse_margin = 8e-6f * (float)(g_max > 1.0 ? g_max : 1.0);
 
+    // Which kernel: large tables / few rotations take the CTA-per-rotation kernel (see below), everything else one warp per
+    // rotation.  sim_cta = 0 never, 1 forces it.
+    const int cta_opt = option(OPT_SIM_CTA);
+    // default: tables too large to stay resident in the warp kernel's shared memory take it when they are very large
+    // or the rotations few; resident tables (<= 6144 rows) only when a launch cannot fill the warp kernel's CTAs
+    // (Fe3C at r = 2, 5 222 rows, 16 384 rotations: 160 us warp per rotation vs 271 us CTA per rotation)
+    const bool cta_auto = n_g >= 4096 && (n_g > SIM_RESIDENT_MAX_G ? (n_g >= 32768 || n_rot <= 2048) : n_rot < 1024);
+    const bool use_cta = n_g > 0 && (cta_opt > 0 || (cta_opt < 0 && cta_auto));
     // scan-line mode: the caller described the table as lattice lines (see include/diffsims_b200.h)
     size_t line_bytes = (size_t)n_lines * 16 + (size_t)((n_lines + 1 + 3) & ~3) * 4;
-    bool lines = n_lines > 0 && line_g0 && line_start && line_step_host && line_bytes <= 96 * 1024 &&
+    bool lines = n_lines > 0 && line_g0 && line_start && line_step_host &&
                  (reinterpret_cast<uintptr_t>(line_g0) & 15) == 0 && (reinterpret_cast<uintptr_t>(line_start) & 15) == 0;
-    // Measured on B200 (tools/bench_configs.py): solving per line only pays when the table is large and a line
-    // crosses the slab in less than about half an index on average; DS_SIM_LINES=0/1 overrides (tests).
+    if (lines && !use_cta) lines = line_bytes <= 96 * 1024;  // (the warp kernel keeps the line tables in shared memory)
+    // DS_SIM_LINES = 0 / 1 overrides the measured rules (tests).
     if (lines) {
         const double rs = inv_wavelength, gm = g_max < rs ? g_max : rs * 0.999999;
         const double slab = 2.0 * s_max + rs - sqrt(rs * rs - gm * gm) + 2.0 * rs * sin(fabs(precession_rad)) * gm / rs;
@@ -845,7 +923,13 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
         const int force = option(OPT_SIM_LINES);
         if (force >= 0)
             lines = force != 0;
+        else if (use_cta)
+            // CTA kernel: a line at angle theta to the beam crosses the slab in slab / (step |cos theta|) rows, ~4.5 slab / step
+            // on average over orientations; the interval expansion pays when that is a small part of a line
+            lines = (double)n_g / n_lines >= 3.0 * (1.0 + 4.5 * slab / step);
         else
+            // warp kernel (tools/bench_configs.py): solving per line only pays when the table is large and a line crosses
+            // the slab in less than about half an index on average
             lines = n_g >= 2048 && slab < 0.5 * step;
     }
     p.n_lines = lines ? n_lines : 0;
@@ -893,12 +977,7 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
     // walk the table in step and share its lines in L1, and nothing is staged through shared memory.  (24 406 rows: equal at
     // 16 384 rotations, 81 vs 131 us at 512.)  sim_cta = 0 never, 1 forces it; sim_stash = candidate capacity of a rotation (small values exercise the fall-back in the tests).
     {
-        const int o = option(OPT_SIM_CTA);
-        // default: tables too large to stay resident in the warp kernel's shared memory take it when they are very large
-        // or the rotations few; resident tables (<= 6144 rows) only when a launch cannot fill the warp kernel's CTAs
-        // (Fe3C at r = 2, 5 222 rows, 16 384 rotations: 160 us warp per rotation vs 271 us CTA per rotation)
-        const bool cta_auto = n_g >= 4096 && (n_g > SIM_RESIDENT_MAX_G ? (n_g >= 32768 || n_rot <= 2048) : n_rot < 1024);
-        if (!lines && n_g > 0 && (o > 0 || (o < 0 && cta_auto))) {
+        if (use_cta) {
             int stash = option(OPT_SIM_STASH);
             if (stash < SIM_CHUNK) stash = 4096;
             int n_chunks = (stash + SIM_CHUNK - 1) / SIM_CHUNK;
@@ -913,20 +992,28 @@ extern "C" int ds_simulate(void *stream, int32_t n_rot, const double *quat, int3
                 const int grid = n_rot < num_sms() * blocks_per_sm ? n_rot : num_sms() * blocks_per_sm;
                 kern<<<grid, SIM_THREADS, smem_c, st>>>(p, n_chunks);
             };
+#define DS_SIM_CTA(M)                                     \
+    do {                                                  \
+        if (lines)                                        \
+            launch_cta(simulate_cta_kernel<M, true>);     \
+        else                                              \
+            launch_cta(simulate_cta_kernel<M, false>);    \
+    } while (0)
             if (precession_rad != 0.0) {
-                launch_cta(simulate_cta_kernel<-1>);
+                DS_SIM_CTA(-1);
             } else {
                 switch (shape_model) {
-                    case DS_SHAPE_BINARY: launch_cta(simulate_cta_kernel<DS_SHAPE_BINARY>); break;
-                    case DS_SHAPE_LINEAR: launch_cta(simulate_cta_kernel<DS_SHAPE_LINEAR>); break;
-                    case DS_SHAPE_SINC: launch_cta(simulate_cta_kernel<DS_SHAPE_SINC>); break;
-                    case DS_SHAPE_SIN2C: launch_cta(simulate_cta_kernel<DS_SHAPE_SIN2C>); break;
-                    case DS_SHAPE_ATANC: launch_cta(simulate_cta_kernel<DS_SHAPE_ATANC>); break;
-                    case DS_SHAPE_LORENTZIAN: launch_cta(simulate_cta_kernel<DS_SHAPE_LORENTZIAN>); break;
-                    case DS_SHAPE_NONE_RETURN_S: launch_cta(simulate_cta_kernel<DS_SHAPE_NONE_RETURN_S>); break;
-                    default: launch_cta(simulate_cta_kernel<-1>); break;  // lorentzian_precession with zero angle
+                    case DS_SHAPE_BINARY: DS_SIM_CTA(DS_SHAPE_BINARY); break;
+                    case DS_SHAPE_LINEAR: DS_SIM_CTA(DS_SHAPE_LINEAR); break;
+                    case DS_SHAPE_SINC: DS_SIM_CTA(DS_SHAPE_SINC); break;
+                    case DS_SHAPE_SIN2C: DS_SIM_CTA(DS_SHAPE_SIN2C); break;
+                    case DS_SHAPE_ATANC: DS_SIM_CTA(DS_SHAPE_ATANC); break;
+                    case DS_SHAPE_LORENTZIAN: DS_SIM_CTA(DS_SHAPE_LORENTZIAN); break;
+                    case DS_SHAPE_NONE_RETURN_S: DS_SIM_CTA(DS_SHAPE_NONE_RETURN_S); break;
+                    default: DS_SIM_CTA(-1); break;  // lorentzian_precession with zero angle
                 }
             }
+#undef DS_SIM_CTA
             return check_launch("ds_simulate (CTA per rotation)");
         }
     }

@@ -339,8 +339,10 @@ def simulate(gt: GTable, quats, wavelength, s_max, width, model, minima_number=5
             count.zero_()
             return SpotTable(count, g_index, xyz, inten, exc, cap)
         # measured (tools/bench_configs.py): once the extinct rows are marked, the plain cull over the packed table
-        # beats the scan-line cull, which rebuilds every row of a line (DS_SIM_LINES=1 still forces it)
-        n_lines = gt.n_lines if (not gt.marked or _cabi.get_option("sim_lines") == 1) else 0
+        # beats the scan-line cull of the warp-per-rotation kernel, which rebuilds every row of a line
+        # (DS_SIM_LINES=1 still forces it); large tables go to the CTA-per-rotation kernel, whose interval expansion
+        # pays with or without marks (ds_simulate decides from the slab / step ratio)
+        n_lines = gt.n_lines if (not gt.marked or gt.n >= 4096 or _cabi.get_option("sim_lines") == 1) else 0
         rc = _cabi.lib().ds_simulate(
             _stream(), n_rot, _cabi.ptr(q), gt.n, _cabi.ptr(gt.xyz), _cabi.ptr(gt.f32), _cabi.ptr(gt.I0),
             float(gt.g_max), 1.0 / float(wavelength), float(s_max), float(width), model_id,

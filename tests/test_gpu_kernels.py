@@ -212,13 +212,17 @@ def test_simulate_cta_per_rotation_is_identical(eng, opts, name, rr, s_max, mode
     wl = K.get_electron_wavelength(200)
     q = random_quats(37, 5)
     q[0] = (1, 0, 0, 0)
-    q[1] = (np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0)
+    q[1] = (np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0)      # c* perpendicular to the beam: lines parallel to the slab
+    q[2] = (np.cos(np.pi / 4 + 2e-4), np.sin(np.pi / 4 + 2e-4), 0, 0)   # almost parallel
     kw = dict(precession_rad=np.deg2rad(prec_deg), want_exc=True, min_intensity=min_int)
     opts(sim_lines=0, sim_cta=0)
     ref = eng.simulate(gt, q, wl, s_max, s_max, model, **kw)
     assert int(ref.count.sum()) > 0
-    for cta, stash in ((1, -1), (1, 512), (1, 64)):
-        opts(sim_cta=cta, sim_stash=stash)
+    # (brute-force scan of the table slices; the interval expansion over lattice lines; small pools; the fall-back)
+    for cta, stash, lines in ((1, -1, 0), (1, -1, 1), (1, 512, 0), (1, 512, 1), (1, 64, 0)):
+        if lines and not gt.n_lines:
+            continue
+        opts(sim_cta=cta, sim_stash=stash, sim_lines=lines)
         got = eng.simulate(gt, q, wl, s_max, s_max, model, cap=ref.cap, **kw)
         assert int(got.max_count) == int(ref.max_count), (cta, stash)
         assert np.array_equal(got.count.cpu().numpy(), ref.count.cpu().numpy()), (cta, stash)

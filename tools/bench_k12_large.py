@@ -46,8 +46,9 @@ print(f"K1 large cell ({b.gtable.n} g x 500 atoms, incl. table packing): factori
 
 q_all = torch.as_tensor(active_quaternions(random_quats(16384, 0)), device=dev)
 b.calibrate_cap(q_all[:2048])
-VARIANTS = [("auto", dict(sim_cta=-1, sim_split=-1)), ("warp/rot x8", dict(sim_cta=0, sim_split=8)),
-            ("warp/rot x2", dict(sim_cta=0, sim_split=2)), ("CTA/rot", dict(sim_cta=1, sim_split=-1))]
+VARIANTS = [("auto", dict(sim_cta=-1, sim_split=-1, sim_lines=-1)), ("warp/rot x8", dict(sim_cta=0, sim_split=8, sim_lines=0)),
+            ("warp/rot x2", dict(sim_cta=0, sim_split=2, sim_lines=0)), ("CTA/rot", dict(sim_cta=1, sim_split=-1, sim_lines=0)),
+            ("CTA/rot lines", dict(sim_cta=1, sim_split=-1, sim_lines=1))]
 for n in (128, 512, 1024, 2048, 16384):
     q = q_all[:n].contiguous()
     line = f"K2 large cell n_rot={n:6d}:"
@@ -56,6 +57,6 @@ for n in (128, 512, 1024, 2048, 16384):
             _cabi.set_option(k, v)
         t = timeit(lambda: b.simulate(q), n=5)
         line += f"  {name}: {t * 1e3:8.1f} us = {t * 1e6 / n:6.1f} ns/rot"
-    for k in ("sim_cta", "sim_split"):
+    for k in ("sim_cta", "sim_split", "sim_lines"):
         _cabi.set_option(k, -1)
     print(line, flush=True)

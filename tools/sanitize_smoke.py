@@ -59,17 +59,19 @@ for lines in (0, 1):
     engine.simulate(plan.run(0.5e-20, compact=False), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 engine.simulate(plan.run(0.5e-20), random_quats(40, 2), gen.wavelength, 0.01, 0.01, "lorentzian")
 _cabi.set_option("sim_lines", -1)
-# few rotations over a large table (one CTA per rotation: default stash, a small pool, the fall-back; 2 warps per CTA),
+# few rotations over a large table (one CTA per rotation: default stash, a small pool, the fall-back, brute-force and
+# scan-line scans; 2 warps per CTA),
 # the factorised structure factors (>= 4096 rows, >= 32 atoms: box kernel), the SO(3) grids
 plan = gen._g_plan(cases.phase("large"), 1.6, True, cases.DW)
 gt_large = plan.run(0.0)
-for cta, stash in ((-1, -1), (1, 512), (1, 64), (0, -1)):
+for cta, stash, lines in ((-1, -1, -1), (1, 512, 0), (1, 512, 1), (1, 64, 0), (1, -1, 1), (0, -1, -1)):
     _cabi.set_option("sim_cta", cta)
     _cabi.set_option("sim_stash", stash)
+    _cabi.set_option("sim_lines", lines)
     engine.simulate(gt_large, random_quats(40, 3), gen.wavelength, 0.01, 0.01, "lorentzian")
     engine.simulate(gt_large, random_quats(9, 4), gen.wavelength, 0.01, 0.01, "sin2c", precession_rad=0.005)
-_cabi.set_option("sim_cta", -1)
-_cabi.set_option("sim_stash", -1)
+for k in ("sim_cta", "sim_stash", "sim_lines"):
+    _cabi.set_option(k, -1)
 from diffsims_b200.generators.rotation_list_generators import fundamental_zone_device, local_grid_device
 fundamental_zone_device(12, point_group="m-3m")
 local_grid_device(10, center=(10, 20, 30), grid_width=30)
