@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(256) render_prepare_rows_kernel(const RenderPa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
     unsigned char *base = smem_raw + (size_t)warp * warp_bytes;
-    unsigned *pkey = reinterpret_cast<unsigned *>(base);  // [cap] column | row << 16 of spot j, ~0 = not in frame
-    float *pamp = reinterpret_cast<float *>(base + (size_t)p.cap * 4);
-    uint2 *sspot = reinterpret_cast<uint2 *>(base + (size_t)p.cap * 8);  // [cap] sorted spots
-    int *bins = reinterpret_cast<int *>(base + (size_t)p.cap * 16);
+    // (shared memory per warp bounds the warps per SM of this latency-bound pass: the amplitudes are re-read from global
+    // memory at scatter time instead of being kept here)
+    uint2 *sspot = reinterpret_cast<uint2 *>(base);                                  // [cap] sorted spots
+    unsigned *pkey = reinterpret_cast<unsigned *>(base + (size_t)p.cap * 8);         // [cap] column | row << 16 of spot j, ~0 = not in frame
+    int *bins = reinterpret_cast<int *>(base + (size_t)p.cap * 12);
     const int R = p.radius, H = p.H, W = p.W;
     const RowsGeom geo = rows_geom(R, H);
 
@@ -132,7 +133,6 @@ __global__ void __launch_bounds__(256) render_prepare_rows_kernel(const RenderPa
                     kk = (unsigned)(int)px | ((unsigned)(int)py << 16);
                 if (kk != 0xffffffffu) atomicAdd(&bins[(kk >> 16) + 1], 1);
                 pkey[j] = kk;
-                pamp[j] = (float)sint[j];
             }
             n_live += __popc(__ballot_sync(0xffffffffu, kk != 0xffffffffu));
         }
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) render_prepare_rows_kernel(const RenderPa
             }
             __syncwarp();
             if (kk != 0xffffffffu) {
-                sspot[at] = make_uint2(kk, __float_as_uint(pamp[j]));
+                sspot[at] = make_uint2(kk, __float_as_uint((float)sint[j]));
                 if ((peers >> lane) == 1u) bins[row] = at + 1;  // the highest lane of the row leaves its end
             }
             __syncwarp();
@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(256) render_prepare_rows_kernel(const RenderPa
 
 static int launch_render_prepare_rows(const RenderParams &p, unsigned char *records, cudaStream_t st) {
     const int record_bytes = rows_record_bytes(p.cap);
-    const int warp_bytes = (p.cap * 16 + PREPR_BINS * 4 + 15) & ~15;
+    const int warp_bytes = (p.cap * 12 + PREPR_BINS * 4 + 15) & ~15;
     int warps = 8;
-    while (warps > 1 && (size_t)warps * warp_bytes > 96 * 1024) warps >>= 1;
+    while (warps > 1 && (size_t)warps * warp_bytes > 110 * 1024) warps >>= 1;   // (two CTAs per SM)
     const size_t smem = (size_t)warps * warp_bytes;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(render_prepare_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(render_prepare_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     const int want = (p.n_tmpl + warps - 1) / warps;
     const int grid = want < 16 * num_sms() ? want : 16 * num_sms();
     render_prepare_rows_kernel<<<grid, warps * 32, smem, st>>>(p, records, record_bytes, warp_bytes);
