@@ -322,7 +322,7 @@ def config_probe(name, dev, peak, n=None):
     w = WORKLOADS[name]
     out = []
     for ph in w["phases"]:
-        n_t = n or max(1024, w["batch"] // (8 if name != "c4" else 2))
+        n_t = n or max(1024, w["batch"] // (4 if name != "c4" else 1))
         b = make_builder(w, ph, dev)
         b.prepare()
         q = torch.as_tensor(active_quaternions(random_quats(n_t, 7)), device=dev)

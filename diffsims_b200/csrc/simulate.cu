@@ -630,13 +630,25 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) simulate_cta_kernel(const SimP
             const float bz = fmaf(mz0, p.step[0], fmaf(mz1, p.step[1], mz2 * p.step[2]));  // dz' per index
             const bool parallel = fabsf(bz) < 1e-3f;
             const float inv_b = parallel ? 0.0f : 1.0f / bz;
+            // (the next batch's line records are requested before this batch is expanded)
+            float4 g0_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            int start_n = 0, end_n = 0;
+            if (L_lo + lane < L_hi) {
+                g0_n = __ldg(p.line_g0 + L_lo + lane);
+                start_n = __ldg(p.line_start + L_lo + lane);
+                end_n = __ldg(p.line_start + L_lo + lane + 1);
+            }
             for (int L0 = L_lo; L0 < L_hi; L0 += 32) {
                 const int Ln = L0 + lane;
                 int first = 0, cnt = 0, ilo = 0;
-                float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 g0 = g0_n;
+                const int start = start_n, len = end_n - start_n;
+                if (Ln + 32 < L_hi) {
+                    g0_n = __ldg(p.line_g0 + Ln + 32);
+                    start_n = __ldg(p.line_start + Ln + 32);
+                    end_n = __ldg(p.line_start + Ln + 33);
+                }
                 if (Ln < L_hi) {
-                    g0 = __ldg(p.line_g0 + Ln);
-                    const int start = __ldg(p.line_start + Ln), len = __ldg(p.line_start + Ln + 1) - start;
                     const float a = fmaf(mz0, g0.x, fmaf(mz1, g0.y, mz2 * g0.z));
                     int ihi;
                     if (!parallel) {
