@@ -751,8 +751,11 @@ def main():
         except Exception:
             traffic = None
     k3_kernels = engine.render_launch_count(builder.cap, builder.shape, builder.sigma, True, builder.mean_spots)
+    # (the dispatch rule of ds_render: per-reflection tcgen05 product from 16 reflections per template, row-binned from 320)
+    rows_kernel = k3_kernels == 2 and (builder.mean_spots or 0.0) >= 320.0
     roofline = dict(kernel="render_pipe_kernel (K3, ds_render)" if k3_kernels == 1 else
-                           "render_prepare_kernel + render_umma_kernel (K3, ds_render, tcgen05)",
+                           ("render_prepare_rows_kernel + render_rows_kernel (K3, ds_render, tcgen05 banded product)" if rows_kernel
+                            else "render_prepare_kernel + render_umma_kernel (K3, ds_render, tcgen05)"),
                     bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=traffic, algorithmic_bytes_per_launch=algo_bytes,
                     kernel_ms=k3_ms, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
