@@ -18,7 +18,7 @@
 //     memory), three products per (half, chunk): A_hi B_hi + A_hi B_lo + A_lo B_hi (float32 accumulation);
 //   * a half that no chunk reaches is zeroed by one product with an all-zero window of the master.
 // 28 warps: front, MMA issue, 16 producers (one per row of a chunk), 8 epilogue; setmaxnreg gives the epilogue warpgroups
-// 112 registers and everyone else 48.  Front warp, epilogue (tcgen05.ld -> max -> scale -> swizzled staging -> TMA store),
+// 112 registers and everyone else 56.  Front warp, epilogue (tcgen05.ld -> max -> scale -> swizzled staging -> TMA store),
 // slots and barriers are those of render_umma.cu; the per-template records come from render_prepare_rows_kernel below (float64 projection, ordering by
 // row with ties in list order, "last write wins" inside a pixel, row offsets, mask of the non-empty chunks).
 //
@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
     const uint32_t tm = s_tmem;
 
     // Role dispatch.  The kernel starts with 72 registers per thread (896 threads); the two epilogue warpgroups (warps
-    // 4..11) raise their allowance to 112 and every other warpgroup lowers it to 48 (an increase can only draw on what the
+    // 4..11) raise their allowance to 112 and every other warpgroup lowers it to 56 (an increase can only draw on what the
     // CTA's own warps released) -- each setmaxnreg sits at the head of the branch it governs (one instruction per
     // warpgroup, and ptxas allocates each branch against its own limit).
     const bool epi_role = warp >= RW_EPI_WARP0 && warp < RW_EPI_WARP0 + RW_EPI;
     if (!epi_role) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // =============================== front warp ==============================================================
         RPROF_DECL;
