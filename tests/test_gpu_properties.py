@@ -151,6 +151,41 @@ def test_config4_large_cell_structure_factors():
         compare_spots(ref, got, s_max=0.01, rr=2.5)
 
 
+def test_config4_large_cell_templates_match_the_oracle():
+    """configs[3] end to end at its own settings (reciprocal_radius 2.5, 256 x 256, sigma 10): ~680 reflections per
+    template go through the row-binned tcgen05 kernel by the density dispatch of ds_render; a sample of templates
+    against the oracle's rasteriser, and the per-reflection tcgen05 kernel against the same."""
+    import torch
+    from diffsims_b200 import _cabi
+    phase = cases.phase("large")
+    gen = ds.SimulationGenerator(200)
+    b = TemplateLibraryBuilder(gen, phase, reciprocal_radius=2.5, max_excitation_error=0.01, shape=(256, 256), sigma=10.0,
+                               calibration=2.5 / 128, debye_waller_factors=cases.DW)
+    b.prepare()
+    dev = engine.device()
+    q_host = active_quaternions(random_quats(200, 17))
+    q = torch.as_tensor(q_host, device=dev)
+    b.calibrate_cap(q)
+    assert b.mean_spots > 320          # the density hint that selects the row-binned kernel
+    spots = b.simulate(q, check_overflow=True)
+    img = torch.empty((200, 256, 256), dtype=torch.float32, device=dev)
+    gs = K.GSet(phase.structure, 2.5, True)
+    saved = _cabi.get_option("render_rows")
+    try:
+        for rows in (-1, 0):
+            _cabi.set_option("render_rows", rows)
+            out = b.render(spots, img).cpu().numpy()
+            for r in (0, 57, 199):
+                ref = K.simulate_rotation(phase.structure, gs, K.quat_to_matrix(q_host[r]).T, gen.wavelength, 0.01,
+                                          debye_waller_factors=cases.DW)
+                pat = K.diffraction_pattern(ref["xyz"], ref["intensity"], (256, 256), sigma=10.0, calibration=2.5 / 128)
+                assert np.abs(out[r] - pat).max() <= IMG_ATOL, (rows, r)
+                assert out[r].max() == 1.0
+    finally:
+        _cabi.set_option("render_rows", saved)
+
+
+
 def test_render_linearity():
     """Unnormalised rendering is linear in the spot list: image(A u B) = image(A) + image(B)."""
     import torch
