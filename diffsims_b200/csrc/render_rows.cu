@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) render_rows_kernel(const Render
                         const uint64_t wo = (uint64_t)(uint32_t)(8 * (16 * h - 2 * c + ((geo.RP - geo.d_min) >> 3)));
                         const uint64_t d_a_hi = d_a_hi0 + wo, d_a_lo = d_a_lo0 + wo;
                         const uint32_t d = tm + (uint32_t)(h * 256);
-                        umma(d, d_a_hi, d_b_hi + so, idesc, first ? 0u : 1u);
-                        umma(d, d_a_hi, d_b_lo + so, idesc, 1);
+                        umma_keep_a(d, d_a_hi, d_b_hi + so, idesc, first ? 0u : 1u);
+                        umma_reuse_a(d, d_a_hi, d_b_lo + so, idesc, 1);
                         umma(d, d_a_lo, d_b_hi + so, idesc, 1);
                         if (last) umma_commit(&s_half_full[h]);  // the half is complete
                     }

@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(um_warps(TEAM) * 32, 1) render_umma_kernel(con
                         const uint32_t idesc = umma_idesc((int)(win >> 16));
                         const uint32_t d = tm + (uint32_t)(h * 256) + (win & 0xffffu);
                         PROF_SEC(0);
-                        umma(d, d_a_hi + so, d_b_hi + so, idesc, j > 0);
-                        umma(d, d_a_hi + so, d_b_lo + so, idesc, 1);
+                        umma_keep_a(d, d_a_hi + so, d_b_hi + so, idesc, j > 0);
+                        umma_reuse_a(d, d_a_hi + so, d_b_lo + so, idesc, 1);
                         umma(d, d_a_lo + so, d_b_hi + so, idesc, 1);
                         umma_commit(&s_stage_empty[stage]);                   // the stage may be refilled
                         if (j == n_chunks - 1) umma_commit(&s_half_full[h]);  // the half is complete

@@ -26,6 +26,26 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with the A operand kept in the tensor core's collector buffer for the next product (KEEP: `fill`) or taken from
+// it instead of shared memory (REUSE: `lastuse`; the previous product must have been issued with KEEP on the same A by this
+// thread).  SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE.  The hi x hi, hi x lo pair of a split product shares A_hi this way:
+// a third less A traffic on the shared-memory pipe, which is what bounds the dense templates.
+__device__ __forceinline__ void umma_keep_a(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_reuse_a(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
